@@ -1,0 +1,578 @@
+// elementwise.cu — the HBM-bound passes of the MoCoGAN step: per-channel reductions (BatchNorm statistics, bias
+// gradients, BN backward sums), the fused affine+activation+noise pass, video packing, tanh backward, Adam.
+// All tensors are channels-last matrices [M][C]; vector kernels move 8 channels (16 B bf16 / 32 B fp32) per thread.
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace mcg {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+std::atomic<long long> g_launches{0};
+
+// =====================================================================================================
+// Column reduction skeleton: two sums per channel, deterministic (per-block partials + ordered finalize).
+// =====================================================================================================
+constexpr int kRedThreads = 256;
+constexpr int kRedMaxBlocks = 592;  // 4 x 148 SMs
+
+static int pow2_ge(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+struct StatsF {  // sum y, sum y^2
+  template <typename T, int VEC>
+  __device__ __forceinline__ void operator()(const T* y, const T*, long long off, int c0, float (&a)[VEC],
+                                             float (&b)[VEC]) const {
+    float v[VEC];
+    if (VEC == 8) ld8<T>(y + off, reinterpret_cast<float(&)[8]>(v));
+    else v[0] = ld<T>(y, off);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { a[i] += v[i]; b[i] += v[i] * v[i]; }
+  }
+};
+struct SumF {  // sum g
+  template <typename T, int VEC>
+  __device__ __forceinline__ void operator()(const T* g, const T*, long long off, int c0, float (&a)[VEC],
+                                             float (&b)[VEC]) const {
+    float v[VEC];
+    if (VEC == 8) ld8<T>(g + off, reinterpret_cast<float(&)[8]>(v));
+    else v[0] = ld<T>(g, off);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) a[i] += v[i];
+  }
+};
+struct BnBwdF {  // sum g', sum g'*xhat with g' = g * act'(scale*y+shift)
+  const float *mean, *invstd, *scale, *shift;
+  int act;
+  float slope;
+  template <typename T, int VEC>
+  __device__ __forceinline__ void operator()(const T* g, const T* y, long long off, int c0, float (&a)[VEC],
+                                             float (&b)[VEC]) const {
+    float gv[VEC], yv[VEC];
+    if (VEC == 8) {
+      ld8<T>(g + off, reinterpret_cast<float(&)[8]>(gv));
+      ld8<T>(y + off, reinterpret_cast<float(&)[8]>(yv));
+    } else {
+      gv[0] = ld<T>(g, off);
+      yv[0] = ld<T>(y, off);
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      int c = c0 + i;
+      float pre = scale[c] * yv[i] + shift[c];
+      float gp = gv[i] * act_grad(act, slope, pre, 0);
+      a[i] += gp;
+      b[i] += gp * (yv[i] - mean[c]) * invstd[c];
+    }
+  }
+};
+
+template <typename T, int VEC, typename F>
+__global__ void __launch_bounds__(kRedThreads) colreduce_kernel(F f, const T* p0, const T* p1, long long M, int C,
+                                                               int tpr, float* __restrict__ partial) {
+  extern __shared__ float red[];  // [rpb][tpr][2*VEC]
+  const int CG = C / VEC;
+  const int rpb = kRedThreads / tpr;
+  const int tx = threadIdx.x % tpr, ty = threadIdx.x / tpr;
+  float a[VEC], b[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) a[i] = b[i] = 0.f;
+  if (tx < CG) {
+    for (long long m = (long long)blockIdx.x * rpb + ty; m < M; m += (long long)gridDim.x * rpb)
+      f.template operator()<T, VEC>(p0, p1, m * C + (long long)tx * VEC, tx * VEC, a, b);
+  }
+  float* mine = red + ((size_t)ty * tpr + tx) * 2 * VEC;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { mine[i] = a[i]; mine[VEC + i] = b[i]; }
+  __syncthreads();
+  if (ty == 0 && tx < CG) {
+    for (int r = 1; r < rpb; ++r) {
+      const float* o = red + ((size_t)r * tpr + tx) * 2 * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { a[i] += o[i]; b[i] += o[VEC + i]; }
+    }
+    float* dst = partial + (size_t)blockIdx.x * 2 * C;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { dst[tx * VEC + i] = a[i]; dst[C + tx * VEC + i] = b[i]; }
+  }
+}
+
+template <typename F>
+static int launch_colreduce(F f, const void* p0, const void* p1, long long M, int C, int dtype, void* ws,
+                            size_t ws_bytes, cudaStream_t st, int* nblk_out, const char* name) {
+  if (M <= 0 || C <= 0) MCG_FAIL(MCG_ERR_SHAPE, "%s: empty matrix M=%lld C=%d", name, M, C);
+  const int VEC = (C % 8 == 0) ? 8 : 1;
+  const int CG = C / VEC;
+  if (CG > kRedThreads) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: C=%d has too many channel groups", name, C);
+  const int tpr = pow2_ge(CG);
+  const int rpb = kRedThreads / tpr;
+  long long want = (M + rpb - 1) / rpb;
+  int nblk = (int)(want < kRedMaxBlocks ? want : kRedMaxBlocks);
+  if (ws_bytes < (size_t)nblk * 2 * C * sizeof(float) || !ws)
+    MCG_FAIL(MCG_ERR_WORKSPACE, "%s: workspace %zu < %zu", name, ws_bytes, (size_t)nblk * 2 * C * sizeof(float));
+  size_t smem = (size_t)kRedThreads * 2 * VEC * sizeof(float);
+  float* part = reinterpret_cast<float*>(ws);
+#define LAUNCH(T, V) colreduce_kernel<T, V, F><<<nblk, kRedThreads, smem, st>>>(f, (const T*)p0, (const T*)p1, M, C, tpr, part)
+  if (dtype == MCG_F32) { if (VEC == 8) LAUNCH(float, 8); else LAUNCH(float, 1); }
+  else if (dtype == MCG_BF16) { if (VEC == 8) LAUNCH(__nv_bfloat16, 8); else LAUNCH(__nv_bfloat16, 1); }
+  else MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: dtype %d", name, dtype);
+#undef LAUNCH
+  MCG_CHECK_LAUNCH(name);
+  *nblk_out = nblk;
+  return 0;
+}
+
+__global__ void bn_stats_finalize(const float* partial, int nblk, int C, double M, const float* gamma,
+                                  const float* beta, float eps, float decay, float* mean, float* invstd,
+                                  float* scale, float* shift, float* avg_mean, float* avg_var) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0, q = 0;
+  for (int b = 0; b < nblk; ++b) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
+  double mu = s / M;
+  double var = q / M - mu * mu;
+  if (var < 0) var = 0;
+  double inv = 1.0 / sqrt(var + (double)eps);
+  mean[c] = (float)mu;
+  invstd[c] = (float)inv;
+  float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+  float sc = ga * (float)inv;
+  if (scale) scale[c] = sc;
+  if (shift) shift[c] = be - (float)mu * sc;
+  if (avg_mean) {
+    double adjust = M / (M - 1.0 > 1.0 ? M - 1.0 : 1.0);
+    avg_mean[c] = decay * avg_mean[c] + (1.f - decay) * (float)mu;
+    avg_var[c] = decay * avg_var[c] + (1.f - decay) * (float)(adjust * (var + (double)eps));
+  }
+}
+__global__ void sum2_finalize(const float* partial, int nblk, int C, float* out_a, float* out_b, int accumulate,
+                              float* acc_a = nullptr, float* acc_b = nullptr) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0, q = 0;
+  for (int b = 0; b < nblk; ++b) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
+  if (out_a) out_a[c] = (accumulate ? out_a[c] : 0.f) + (float)s;
+  if (out_b) out_b[c] = (accumulate ? out_b[c] : 0.f) + (float)q;
+  if (acc_a) acc_a[c] += (float)s;
+  if (acc_b) acc_b[c] += (float)q;
+}
+
+// =====================================================================================================
+// affine + activation + noise
+// =====================================================================================================
+template <typename TI, typename TO, int VEC>
+__global__ void __launch_bounds__(256) affine_act_noise_kernel(
+    const TI* __restrict__ y, long long M, int C, long long P, const float* __restrict__ scale,
+    const float* __restrict__ shift, int act, float slope, float sigma, const float* __restrict__ noise,
+    long long ns_n, long long ns_c, long long ns_p, const StepState* __restrict__ rng, int call_id,
+    TO* __restrict__ out) {
+  const int CG = C / VEC;
+  const long long total = M * CG;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long m = idx / CG;
+    int c0 = (int)(idx % CG) * VEC;
+    float v[VEC];
+    if (VEC == 8) ld8<TI>(y + m * C + c0, reinterpret_cast<float(&)[8]>(v));
+    else v[0] = ld<TI>(y, m * C + c0);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float pre = scale ? scale[c0 + i] * v[i] + shift[c0 + i] : v[i];
+      v[i] = act_fwd(act, slope, pre);
+    }
+    if (noise) {
+      long long n = m / P, p = m % P;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[i] += sigma * noise[n * ns_n + (long long)(c0 + i) * ns_c + p * ns_p];
+    } else if (rng && sigma != 0.f) {
+      if (VEC == 8) {
+        float z[4];
+        philox_normal4(rng, call_id, (unsigned long long)idx * 2, z);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] += sigma * z[i];
+        philox_normal4(rng, call_id, (unsigned long long)idx * 2 + 1, z);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[4 + (VEC == 8 ? i : 0)] += sigma * z[i];
+      } else {
+        float z[4];
+        philox_normal4(rng, call_id, (unsigned long long)idx, z);
+        v[0] += sigma * z[0];
+      }
+    }
+    if (VEC == 8) st8<TO>(out + m * C + c0, reinterpret_cast<const float(&)[8]>(v));
+    else st<TO>(out, m * C + c0, v[0]);
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) pack_video_kernel(
+    const TI* __restrict__ src, int N, int C, int T, int H, int W, long long s_n, long long s_c, long long s_t,
+    long long s_h, long long s_w, const int* __restrict__ frame_ptr, float sigma, const float* __restrict__ noise,
+    long long ns_n, long long ns_c, long long ns_p, const StepState* __restrict__ rng, int call_id,
+    TO* __restrict__ out) {
+  const int Tout = frame_ptr ? 1 : T;
+  const int t0 = frame_ptr ? *frame_ptr : 0;
+  const long long total = (long long)N * Tout * H * W * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % C);
+    long long r = idx / C;
+    int w = (int)(r % W); r /= W;
+    int h = (int)(r % H); r /= H;
+    int t = (int)(r % Tout);
+    long long n = r / Tout;
+    float v = ld<TI>(src, n * s_n + (long long)c * s_c + (long long)(t + t0) * s_t + (long long)h * s_h + (long long)w * s_w);
+    if (noise) {
+      long long p = ((long long)t * H + h) * W + w;  // position inside the (T',H,W) block the noise tensor covers
+      v += sigma * noise[n * ns_n + (long long)c * ns_c + p * ns_p];
+    } else if (rng && sigma != 0.f) {
+      float z[4];
+      philox_normal4(rng, call_id, (unsigned long long)idx, z);
+      v += sigma * z[0];
+    }
+    st<TO>(out, idx, v);
+  }
+}
+
+// =====================================================================================================
+// backward of (BN ->) activation, apply half
+// =====================================================================================================
+template <typename TI, typename TO, int VEC>
+__global__ void __launch_bounds__(256) act_bn_bwd_apply_kernel(
+    const TI* __restrict__ g, const TI* __restrict__ y, long long M, int C, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ scale,
+    const float* __restrict__ shift, int act, float slope, int use_output, const float* __restrict__ dgamma,
+    const float* __restrict__ dbeta, float inv_m, TO* __restrict__ gy) {
+  const int CG = C / VEC;
+  const long long total = M * CG;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long m = idx / CG;
+    int c0 = (int)(idx % CG) * VEC;
+    float gv[VEC], yv[VEC];
+    if (VEC == 8) {
+      ld8<TI>(g + m * C + c0, reinterpret_cast<float(&)[8]>(gv));
+      ld8<TI>(y + m * C + c0, reinterpret_cast<float(&)[8]>(yv));
+    } else {
+      gv[0] = ld<TI>(g, m * C + c0);
+      yv[0] = ld<TI>(y, m * C + c0);
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      int c = c0 + i;
+      if (mean) {
+        float pre = scale[c] * yv[i] + shift[c];
+        float gp = gv[i] * act_grad(act, slope, pre, 0);
+        float xh = (yv[i] - mean[c]) * invstd[c];
+        gv[i] = gamma[c] * invstd[c] * (gp - (xh * dgamma[c] + dbeta[c]) * inv_m);
+      } else {
+        gv[i] = gv[i] * act_grad(act, slope, yv[i], use_output);
+      }
+    }
+    if (VEC == 8) st8<TO>(gy + m * C + c0, reinterpret_cast<const float(&)[8]>(gv));
+    else st<TO>(gy, m * C + c0, gv[0]);
+  }
+}
+
+template <typename TG, typename TO, typename TD>
+__global__ void __launch_bounds__(256) tanh_bwd_video_kernel(const TG* __restrict__ gv, const TG* __restrict__ gi,
+                                                             const TO* __restrict__ out_tn, int N, int T, int HW,
+                                                             int C, const int* __restrict__ frame_ptr,
+                                                             TD* __restrict__ g_tn) {
+  const int ft = frame_ptr ? *frame_ptr : -1;
+  const long long per = (long long)HW * C;
+  const long long total = (long long)T * N * per;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long e = idx % per;
+    long long r = idx / per;
+    int n = (int)(r % N);
+    int t = (int)(r / N);
+    float g = gv ? ld<TG>(gv, ((long long)n * T + t) * per + e) : 0.f;
+    if (gi && t == ft) g += ld<TG>(gi, (long long)n * per + e);
+    float o = ld<TO>(out_tn, idx);
+    st<TD>(g_tn, idx, g * (1.f - o * o));
+  }
+}
+
+// =====================================================================================================
+// Adam + WeightDecay, casts, RNG utilities, step state
+// =====================================================================================================
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v,
+                                                   __nv_bfloat16* __restrict__ pb, long long n, float alpha,
+                                                   float beta1, float beta2, float eps, float wd, float gscale,
+                                                   const int* __restrict__ t_ptr) {
+  __shared__ float lr_s;
+  if (threadIdx.x == 0) {
+    double t = (double)(*t_ptr);
+    double fix1 = 1.0 - pow((double)beta1, t), fix2 = 1.0 - pow((double)beta2, t);
+    lr_s = (float)((double)alpha * sqrt(fix2) / fix1);
+  }
+  __syncthreads();
+  const float lr = lr_s, omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float pi = p[i];
+    float gi = gscale * g[i] + wd * pi;
+    float mi = m[i], vi = v[i];
+    mi += omb1 * (gi - mi);
+    vi += omb2 * (gi * gi - vi);
+    pi -= lr * mi / (sqrtf(vi) + eps);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi;
+    if (pb) pb[i] = __float2bfloat16_rn(pi);
+  }
+}
+__global__ void cast_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = __float2bfloat16_rn(s[i]);
+}
+__global__ void state_init_kernel(StepState* s, unsigned long long seed) {
+  s->seed_lo = (uint32_t)seed; s->seed_hi = (uint32_t)(seed >> 32);
+  s->step = 0; s->frame_t = 0; s->adam_t = 0; s->r0 = s->r1 = s->r2 = 0;
+}
+__global__ void state_advance_kernel(StepState* s, int T) {
+  s->step += 1;
+  s->adam_t += 1;
+  uint4 r = philox4x32(make_uint4(0, 0, 0x7fffffff, s->step), make_uint2(s->seed_lo, s->seed_hi));
+  s->frame_t = T > 0 ? r.x % (uint32_t)T : 0;
+}
+__global__ void randn_kernel(float* out, long long n, float sigma, const StepState* rng, int call_id) {
+  long long n4 = (n + 3) / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float z[4];
+    philox_normal4(rng, call_id, (unsigned long long)i, z);
+    for (int j = 0; j < 4; ++j)
+      if (i * 4 + j < n) out[i * 4 + j] = sigma * z[j];
+  }
+}
+__global__ void randint_kernel(int* out, long long n, int high, const StepState* rng, int call_id) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint4 r = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)call_id, rng->step),
+                         make_uint2(rng->seed_lo, rng->seed_hi));
+    out[i] = (int)(r.x % (uint32_t)high);
+  }
+}
+
+static int grid_for(long long work, int threads = 256) {
+  long long b = (work + threads - 1) / threads;
+  long long cap = (long long)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace mcg
+
+using namespace mcg;
+
+static bool dtype_ok(int d) { return d == MCG_F32 || d == MCG_BF16; }
+
+// runtime dtype -> compile-time type tags
+template <typename F> static void dispatch1(int d, F&& f) {
+  if (d == MCG_F32) f(float{});
+  else f(__nv_bfloat16{});
+}
+template <typename F> static void dispatch2(int d0, int d1, F&& f) {
+  dispatch1(d0, [&](auto a) { dispatch1(d1, [&](auto b) { f(a, b); }); });
+}
+
+extern "C" {
+
+int mcg_version(void) { return MCG_VERSION; }
+const char* mcg_last_error(void) { return g_err; }
+long long mcg_launch_count(void) { return g_launches.load(); }
+
+size_t mcg_colreduce_workspace_bytes(long long M, int C) {
+  (void)M;
+  return (size_t)kRedMaxBlocks * 2 * (size_t)(C > 0 ? C : 1) * sizeof(float);
+}
+
+int mcg_bn_stats(const void* y, long long M, int C, int dtype, const float* gamma, const float* beta, float eps,
+                 float decay, float* mean, float* invstd, float* scale, float* shift, float* avg_mean, float* avg_var,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!y || !mean || !invstd) MCG_FAIL(MCG_ERR_SHAPE, "mcg_bn_stats: null pointer");
+  int nblk = 0;
+  int rc = launch_colreduce(StatsF{}, y, nullptr, M, C, dtype, workspace, workspace_bytes, as_stream(stream), &nblk,
+                            "mcg_bn_stats");
+  if (rc) return rc;
+  bn_stats_finalize<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>((const float*)workspace, nblk, C, (double)M, gamma,
+                                                                    beta, eps, decay, mean, invstd, scale, shift,
+                                                                    avg_mean, avg_var);
+  MCG_CHECK_LAUNCH("mcg_bn_stats(finalize)");
+  return 0;
+}
+
+int mcg_colsum(const void* g, long long M, int C, int dtype, float* out, int accumulate, void* workspace,
+               size_t workspace_bytes, void* stream) {
+  if (!g || !out) MCG_FAIL(MCG_ERR_SHAPE, "mcg_colsum: null pointer");
+  int nblk = 0;
+  int rc = launch_colreduce(SumF{}, g, nullptr, M, C, dtype, workspace, workspace_bytes, as_stream(stream), &nblk,
+                            "mcg_colsum");
+  if (rc) return rc;
+  sum2_finalize<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>((const float*)workspace, nblk, C, out, nullptr,
+                                                                accumulate);
+  MCG_CHECK_LAUNCH("mcg_colsum(finalize)");
+  return 0;
+}
+
+int mcg_act_bn_bwd_reduce(const void* g, const void* y, long long M, int C, int dtype, const float* mean,
+                          const float* invstd, const float* scale, const float* shift, int act, float slope,
+                          float* dgamma, float* dbeta, float* acc_dgamma, float* acc_dbeta, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (!g || !y || !mean || !invstd || !scale || !shift || !dgamma || !dbeta)
+    MCG_FAIL(MCG_ERR_SHAPE, "mcg_act_bn_bwd_reduce: null pointer");
+  int nblk = 0;
+  BnBwdF f{mean, invstd, scale, shift, act, slope};
+  int rc = launch_colreduce(f, g, y, M, C, dtype, workspace, workspace_bytes, as_stream(stream), &nblk,
+                            "mcg_act_bn_bwd_reduce");
+  if (rc) return rc;
+  // partial[.,0,:] = sum g' -> dbeta ; partial[.,1,:] = sum g' xhat -> dgamma; acc_* are the parameter
+  // gradients, which accumulate across the real and fake calls of one pass as in Chainer.
+  sum2_finalize<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>((const float*)workspace, nblk, C, dbeta, dgamma, 0,
+                                                                acc_dbeta, acc_dgamma);
+  MCG_CHECK_LAUNCH("mcg_act_bn_bwd_reduce(finalize)");
+  return 0;
+}
+
+int mcg_affine_act_noise(const void* y, long long M, int C, long long P, int dtype, const float* scale,
+                         const float* shift, int act, float slope, float sigma, const float* noise, long long ns_n,
+                         long long ns_c, long long ns_p, const void* rng_state, int call_id, void* out, int out_dtype,
+                         void* stream) {
+  if (!y || !out || M <= 0 || C <= 0 || P <= 0) MCG_FAIL(MCG_ERR_SHAPE, "mcg_affine_act_noise: bad arguments");
+  if (!dtype_ok(dtype) || !dtype_ok(out_dtype)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_affine_act_noise: dtype");
+  if ((scale == nullptr) != (shift == nullptr)) MCG_FAIL(MCG_ERR_SHAPE, "mcg_affine_act_noise: scale/shift mismatch");
+  cudaStream_t st = as_stream(stream);
+  const StepState* rng = (const StepState*)rng_state;
+  dispatch2(dtype, out_dtype, [&](auto ti, auto to) {
+    using TI = decltype(ti);
+    using TO = decltype(to);
+    if (C % 8 == 0)
+      affine_act_noise_kernel<TI, TO, 8><<<grid_for(M * (C / 8)), 256, 0, st>>>(
+          (const TI*)y, M, C, P, scale, shift, act, slope, sigma, noise, ns_n, ns_c, ns_p, rng, call_id, (TO*)out);
+    else
+      affine_act_noise_kernel<TI, TO, 1><<<grid_for(M * C), 256, 0, st>>>(
+          (const TI*)y, M, C, P, scale, shift, act, slope, sigma, noise, ns_n, ns_c, ns_p, rng, call_id, (TO*)out);
+  });
+  MCG_CHECK_LAUNCH("mcg_affine_act_noise");
+  return 0;
+}
+
+int mcg_pack_video(const void* src, int src_dtype, int N, int C, int T, int H, int W, long long s_n, long long s_c,
+                   long long s_t, long long s_h, long long s_w, const int* frame_ptr, float sigma, const float* noise,
+                   long long ns_n, long long ns_c, long long ns_p, const void* rng_state, int call_id, void* out,
+                   int out_dtype, void* stream) {
+  if (!src || !out || N <= 0 || C <= 0 || T <= 0 || H <= 0 || W <= 0)
+    MCG_FAIL(MCG_ERR_SHAPE, "mcg_pack_video: bad arguments");
+  if (!dtype_ok(src_dtype) || !dtype_ok(out_dtype)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_pack_video: dtype");
+  cudaStream_t st = as_stream(stream);
+  long long total = (long long)N * (frame_ptr ? 1 : T) * H * W * C;
+  dispatch2(src_dtype, out_dtype, [&](auto ti, auto to) {
+    using TI = decltype(ti);
+    using TO = decltype(to);
+    pack_video_kernel<TI, TO><<<grid_for(total), 256, 0, st>>>((const TI*)src, N, C, T, H, W, s_n, s_c, s_t, s_h, s_w,
+                                                               frame_ptr, sigma, noise, ns_n, ns_c, ns_p,
+                                                               (const StepState*)rng_state, call_id, (TO*)out);
+  });
+  MCG_CHECK_LAUNCH("mcg_pack_video");
+  return 0;
+}
+
+int mcg_act_bn_bwd_apply(const void* g, const void* y, long long M, int C, int dtype, const float* mean,
+                         const float* invstd, const float* gamma, const float* scale, const float* shift, int act,
+                         float slope, int use_output, const float* dgamma, const float* dbeta, void* gy, int out_dtype,
+                         void* stream) {
+  if (!g || !y || !gy || M <= 0 || C <= 0) MCG_FAIL(MCG_ERR_SHAPE, "mcg_act_bn_bwd_apply: bad arguments");
+  if (mean && (!invstd || !gamma || !scale || !shift || !dgamma || !dbeta))
+    MCG_FAIL(MCG_ERR_SHAPE, "mcg_act_bn_bwd_apply: BN mode needs invstd/gamma/scale/shift/dgamma/dbeta");
+  if (!dtype_ok(dtype) || !dtype_ok(out_dtype)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_act_bn_bwd_apply: dtype");
+  cudaStream_t st = as_stream(stream);
+  float inv_m = 1.0f / (float)M;
+  dispatch2(dtype, out_dtype, [&](auto ti, auto to) {
+    using TI = decltype(ti);
+    using TO = decltype(to);
+    if (C % 8 == 0)
+      act_bn_bwd_apply_kernel<TI, TO, 8><<<grid_for(M * (C / 8)), 256, 0, st>>>(
+          (const TI*)g, (const TI*)y, M, C, mean, invstd, gamma, scale, shift, act, slope, use_output, dgamma, dbeta,
+          inv_m, (TO*)gy);
+    else
+      act_bn_bwd_apply_kernel<TI, TO, 1><<<grid_for(M * C), 256, 0, st>>>(
+          (const TI*)g, (const TI*)y, M, C, mean, invstd, gamma, scale, shift, act, slope, use_output, dgamma, dbeta,
+          inv_m, (TO*)gy);
+  });
+  MCG_CHECK_LAUNCH("mcg_act_bn_bwd_apply");
+  return 0;
+}
+
+int mcg_tanh_bwd_video(const void* gv, const void* gi, int g_dtype, const void* out_tn, int out_dtype, int N, int T,
+                       int HW, int C, const int* frame_ptr, void* g_tn, int gout_dtype, void* stream) {
+  if (!out_tn || !g_tn || (!gv && !gi) || N <= 0 || T <= 0 || HW <= 0 || C <= 0)
+    MCG_FAIL(MCG_ERR_SHAPE, "mcg_tanh_bwd_video: bad arguments");
+  if (!dtype_ok(g_dtype) || !dtype_ok(out_dtype) || !dtype_ok(gout_dtype))
+    MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_tanh_bwd_video: dtype");
+  cudaStream_t st = as_stream(stream);
+  long long total = (long long)T * N * HW * C;
+  dispatch2(g_dtype, out_dtype, [&](auto tg, auto to) {
+    using TG = decltype(tg);
+    using TO = decltype(to);
+    dispatch1(gout_dtype, [&](auto td) {
+      using TD = decltype(td);
+      tanh_bwd_video_kernel<TG, TO, TD><<<grid_for(total), 256, 0, st>>>((const TG*)gv, (const TG*)gi, (const TO*)out_tn,
+                                                                         N, T, HW, C, frame_ptr, (TD*)g_tn);
+    });
+  });
+  MCG_CHECK_LAUNCH("mcg_tanh_bwd_video");
+  return 0;
+}
+
+int mcg_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float alpha, float beta1,
+                  float beta2, float eps, float wd, float grad_scale, const int* t_ptr, void* stream) {
+  if (!p || !g || !m || !v || !t_ptr || n <= 0) MCG_FAIL(MCG_ERR_SHAPE, "mcg_adam_step: bad arguments");
+  adam_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, alpha, beta1, beta2,
+                                                          eps, wd, grad_scale, t_ptr);
+  MCG_CHECK_LAUNCH("mcg_adam_step");
+  return 0;
+}
+
+int mcg_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+  if (!src || !dst || n <= 0) MCG_FAIL(MCG_ERR_SHAPE, "mcg_cast_f32_to_bf16: bad arguments");
+  cast_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, n);
+  MCG_CHECK_LAUNCH("mcg_cast_f32_to_bf16");
+  return 0;
+}
+
+int mcg_step_state_init(void* state, unsigned long long seed, void* stream) {
+  if (!state) MCG_FAIL(MCG_ERR_SHAPE, "mcg_step_state_init: null state");
+  state_init_kernel<<<1, 1, 0, as_stream(stream)>>>((StepState*)state, seed);
+  MCG_CHECK_LAUNCH("mcg_step_state_init");
+  return 0;
+}
+int mcg_step_advance(void* state, int T, void* stream) {
+  if (!state) MCG_FAIL(MCG_ERR_SHAPE, "mcg_step_advance: null state");
+  state_advance_kernel<<<1, 1, 0, as_stream(stream)>>>((StepState*)state, T);
+  MCG_CHECK_LAUNCH("mcg_step_advance");
+  return 0;
+}
+int mcg_randn(float* out, long long n, float sigma, const void* rng_state, int call_id, void* stream) {
+  if (!out || !rng_state || n <= 0) MCG_FAIL(MCG_ERR_SHAPE, "mcg_randn: bad arguments");
+  randn_kernel<<<grid_for((n + 3) / 4), 256, 0, as_stream(stream)>>>(out, n, sigma, (const StepState*)rng_state, call_id);
+  MCG_CHECK_LAUNCH("mcg_randn");
+  return 0;
+}
+int mcg_randint(int* out, long long n, int high, const void* rng_state, int call_id, void* stream) {
+  if (!out || !rng_state || n <= 0 || high <= 0) MCG_FAIL(MCG_ERR_SHAPE, "mcg_randint: bad arguments");
+  randint_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(out, n, high, (const StepState*)rng_state, call_id);
+  MCG_CHECK_LAUNCH("mcg_randint");
+  return 0;
+}
+
+}  // extern "C"
