@@ -1,6 +1,7 @@
 """Typed wrappers over the C ABI (include/mcg.h): torch CUDA tensors in, kernels enqueued on torch's current stream.
 torch is used for device memory and streams only — every operation here is a libmcg.so kernel."""
 import ctypes as C
+import os
 
 import torch
 
@@ -58,6 +59,8 @@ def workspace(nbytes, device):
 
 
 def tc_ok(g):
+    if os.environ.get("MCG_DISABLE_TC"):   # debugging aid: route every convolution through the CUDA-core kernel
+        return False
     return (g.Cin % 64 == 0 and g.Cout % 64 == 0 and max(g.sT, g.sH, g.sW) <= 2 and g.kT * g.kH * g.kW <= 64
             and (g.kT * g.kH * g.kW * (g.Cin // 64)) % 2 == 0)
 

@@ -1,0 +1,145 @@
+"""model/updater.py of raahii/mocogan-chainer, re-hosted on libmcg.so (updater.py:9-113).
+
+Same constructor kwargs and method names.  One forward, then the three loss -> cleargrads -> backward -> WeightDecay
+-> Adam passes in the reference's order A (image_dis), B (video_dis), C (image_gen), with in-place weight updates and
+no re-run of the discriminators, so pass C differentiates through updated weights with the activations of the
+forward (SURVEY.md §3.2 pt 3).  Back-propagation whose result the reference discards is not executed (pts 2, 4).
+"""
+import numpy as np
+import torch
+
+from .. import chainer
+from .. import random as mrandom
+from ..chainer import Variable
+from ..chainer import functions as F
+from ..chainer.dataset import concat_examples
+
+
+class Updater(chainer.training.StandardUpdater):
+    def __init__(self, *args, **kwargs):
+        self.model = kwargs.pop('model')
+        self.image_gen, self.image_dis, self.video_dis = kwargs.pop('models')
+        self.video_length = kwargs.pop('video_length')
+        self.img_size = kwargs.pop('img_size')
+        self.channel = kwargs.pop('channel')
+        self.dim_zl = kwargs.pop('dim_zl')
+        self.tf_writer = kwargs.pop('tensorboard_writer')
+        # additive (not in the reference): CUDA-graph capture of the device part of the step
+        self.use_graph = kwargs.pop('use_graph', False)
+        self.graph_warmup = kwargs.pop('graph_warmup', 2)
+
+        super(Updater, self).__init__(*args, **kwargs)
+        self.losses = {}
+        self._graph = None
+        self._static = None
+        self._eager_steps = 0
+
+    # ------------------------------------------------------------------ losses
+    def loss_dis(self, dis, y_real, y_fake, t_real, t_fake):
+        # gan criterion + (infogan, VideoDiscriminator only) categorical criterion — updater.py:25-37, one kernel
+        use_ce = self.model == 'infogan' and dis.name == "VideoDiscriminator"
+        loss = F.gan_loss_dis(y_real, y_fake, _lab(t_real), _lab(t_fake), use_ce)
+        self.losses[dis.name] = loss.data
+        self._report(dis, loss)
+        return loss
+
+    def loss_gen(self, gen, y_fake_i, y_fake_v, t_fake):
+        # updater.py:50-56, one kernel
+        loss = F.gan_loss_gen(y_fake_i, y_fake_v, _lab(t_fake), self.model == 'infogan')
+        self.losses[gen.name] = loss.data
+        self._report(gen, loss)
+        return loss
+
+    def _report(self, link, loss):
+        # updater.py:39-42,58-61: only on a new epoch, so the loss scalar is read back once per epoch, not per step
+        if self.is_new_epoch and self._graph is None and not torch.cuda.is_current_stream_capturing():
+            chainer.report({'loss': loss.data}, link)
+            if self.tf_writer is not None:
+                self.tf_writer.add_scalar('loss:{}'.format(link.name), float(loss.data), self.epoch)
+
+    def concat_label_video(self, video, label, xp=None):
+        """updater.py:65-76 (cgan): append dim_zl planes of -1 with +1 at the label plane."""
+        v = video.data if isinstance(video, Variable) else video
+        lab = label.data if isinstance(label, Variable) else label
+        N, C, T, H, W = v.shape
+        planes = -torch.ones((N, self.dim_zl, T, H, W), dtype=v.dtype, device=v.device)
+        planes[torch.arange(N, device=v.device), lab.long()] = 1.
+        return Variable(torch.cat((v, planes), dim=1), requires_grad=False)
+
+    # ------------------------------------------------------------------ one step on device-resident inputs
+    def step_on_device(self, x_real, t_real):
+        """updater.py:96-113 given the real batch already on the device: x_real (N,C,T,H,W), t_real int32 (N) | None."""
+        image_gen_optimizer = self.get_optimizer('image_gen')
+        image_dis_optimizer = self.get_optimizer('image_dis')
+        video_dis_optimizer = self.get_optimizer('video_dis')
+        image_gen = self.image_gen
+        image_dis, video_dis = self.image_dis, self.video_dis
+        src = mrandom.get_source()
+        src.begin_step()
+        batchsize = x_real.shape[0]
+
+        x_real = Variable(x_real, requires_grad=False)   # the reference's default requires_grad=True is dead work
+        t_real = None if t_real is None else Variable(t_real, requires_grad=False)
+        if self.model == 'cgan':
+            x_real = self.concat_label_video(x_real, t_real)
+        t = src.frame()                                   # updater.py:96, stays on the device
+        y_real_i = image_dis(x_real, frame=t)             # updater.py:97
+        y_real_v = video_dis(x_real)                      # updater.py:98
+
+        ## fake data
+        x_fake, t_fake = image_gen(batchsize)             # updater.py:101  (T,N,C,H,W)
+        x_fake = x_fake.transpose(1, 2, 0, 3, 4)          # updater.py:102  (N,C,T,H,W), still attached to G
+        t_fake = None if t_fake is None else Variable(t_fake, requires_grad=False)
+        if self.model == 'cgan':
+            raise NotImplementedError("cgan needs the label planes on the attached fake clip (SURVEY.md §8f rank 4)")
+        y_fake_i = image_dis(x_fake, frame=t)             # updater.py:107
+        y_fake_v = video_dis(x_fake)                      # updater.py:108
+
+        ## update  (updater.py:111-113)
+        # passes A, B: gradients flowing from the discriminator losses into the generator are discarded by the
+        # reference (image_gen.cleargrads() in pass C) -> not computed.  pass C: discriminator wgrads are discarded.
+        image_dis_optimizer.stop_variables = video_dis_optimizer.stop_variables = (x_fake,)
+        image_gen_optimizer.frozen_links = (image_dis, video_dis)
+        image_dis_optimizer.update(self.loss_dis, image_dis, y_real_i, y_fake_i, t_real, t_fake)
+        video_dis_optimizer.update(self.loss_dis, video_dis, y_real_v, y_fake_v, t_real, t_fake)
+        image_gen_optimizer.update(self.loss_gen, image_gen, y_fake_i, y_fake_v, t_fake)
+
+    # ------------------------------------------------------------------ update_core
+    def update_core(self):
+        ## real data  (updater.py:87-92)
+        batch = self.get_iterator('main').next()
+        x_real, t_real = concat_examples(batch)
+        x_real = self.converter(x_real, self.device)
+        if t_real is not None:
+            t_real = self.converter(np.asarray(t_real).astype(np.int32), self.device)
+        self.step_host_inputs(x_real, t_real)
+
+    def step_host_inputs(self, x_real, t_real):
+        if not self.use_graph:
+            return self.step_on_device(x_real, t_real)
+        # ---- CUDA-graph path: static input buffers, capture once, replay afterwards
+        if self._static is None:
+            self._static = (torch.empty_like(x_real), None if t_real is None else torch.empty_like(t_real))
+        sx, st = self._static
+        sx.copy_(x_real, non_blocking=True)
+        if st is not None:
+            st.copy_(t_real, non_blocking=True)
+        if self._graph is not None:
+            self._graph.replay()
+            return
+        if self._eager_steps < self.graph_warmup:
+            self._eager_steps += 1
+            return self.step_on_device(sx, st)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step_on_device(sx, st)
+        self._graph = g
+        g.replay()
+
+
+def _lab(t):
+    if t is None:
+        return None
+    d = t.data if isinstance(t, Variable) else t
+    return d if d.dtype == torch.int32 else d.int()

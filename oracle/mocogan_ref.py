@@ -287,10 +287,13 @@ class Updater:
             "video_dis": ops.AdamState(video_dis.params, alpha, beta1, weight_decay=weight_decay),
         }
 
-    def update_core(self, x_real, t_real, r, as_executed=False, trace=None):
+    def update_core(self, x_real, t_real, r, as_executed=False, trace=None, d_override=None):
         """One training step.  `as_executed=True` additionally performs the back-propagation work the
         reference executes and then discards (SURVEY.md §3.2 pts 2,4) — used only for CPU-baseline timing.
-        `trace`, if a dict, receives intermediate tensors for per-layer parity tests."""
+        `trace`, if a dict, receives intermediate tensors for per-layer parity tests.
+        `d_override` ({'image_dis': params, 'video_dis': params}) replaces the discriminators' post-update weights
+        just before pass C: Adam's m/(sqrt(v)+eps) turns 1e-6-level gradient differences into 1e-5-level weight
+        differences, so a test that wants to judge pass C's kernels alone feeds both sides the same updated weights."""
         G, Di, Dv = self.image_gen, self.image_dis, self.video_dis
         N = x_real.shape[0]
         t = r["t"]
@@ -330,6 +333,10 @@ class Updater:
             dead_generator_backward(gxf)
         self.opt["video_dis"].update(Dv.params, grads_dv)
         # PASS C — updater.py:113: fresh D weights, stale activations
+        if d_override is not None:
+            for net, key in ((Di, "image_dis"), (Dv, "video_dis")):
+                for k, v in d_override[key].items():
+                    net.params[k][...] = v
         loss_g, gi, gv = loss_gen(self.model, y_fake_i, y_fake_v, t_fake)
         _, gx_i = Di.backward(c_fi, gi, need_gx=True, need_gw=as_executed)
         _, gx_v = Dv.backward(c_fv, gv, need_gx=True, need_gw=as_executed)
