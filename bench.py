@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — MoCoGAN train steps/s on B200 (BASELINE.json metric), one process per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            our arm: libmcg.so kernels, CUDA-graph step
+  python bench.py --impl reference --gpus N --steps K ...  reference arm: the Chainer/NumPy CPU algorithm (oracle
+                                                           port; Chainer 3.1.0 itself cannot run here) on host cores
+
+Workload (config.workload): BASELINE config 2 — normal model as train.py builds it on MUG
+(ImageGenerator(50,10,6,3,64,16), ImageDiscriminator(3,1,64,True,0.2), VideoDiscriminator(3,1,64,True,0.2)),
+synthetic clips (35,3,16,64,64) per GPU, one step = one Updater.update_core (G, Di, Dv each updated once).
+`value` = batch-35 steps per second summed over ranks (weak scaling), inputs already in HBM, device-timed.
+`e2e`   = the same through the public API (Updater.update(): iterator -> pinned host batch -> H2D -> step -> D2H of
+          the three losses every step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+USEFUL_GF_PER_STEP = 1839.2     # algorithmic FLOPs of one useful step at batch 35 (normal model)
+AS_EXECUTED_GF_PER_STEP = 2545.9
+BATCH = 35
+CLIP = (3, 16, 64, 64)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+class PinnedClipIterator(object):
+    """Synthetic MUG-shaped data: a ring of pre-stacked batches in PINNED host memory (float32 (N,3,16,64,64) in
+    [-1,1), labels in [0,6)) — the output contract of datasets.py:105-107 after concat_examples."""
+
+    def __init__(self, batch, seed, ring=4):
+        import torch
+        rng = np.random.default_rng(seed)
+        self.x, self.t = [], []
+        for _ in range(ring):
+            x = torch.from_numpy(rng.uniform(-1, 1, size=(batch,) + CLIP).astype(np.float32)).pin_memory()
+            t = torch.from_numpy(rng.integers(0, 6, size=batch).astype(np.int32)).pin_memory()
+            self.x.append(x)
+            self.t.append(t)
+        self.i, self.epoch, self.is_new_epoch, self.epoch_detail = 0, 0, False, 0.0
+        self.batch_size = batch
+
+    def next(self):
+        k = self.i % len(self.x)
+        self.i += 1
+        return PreStacked(self.x[k], self.t[k])
+
+    __next__ = next
+
+
+class PreStacked(list):
+    """A batch that is already concatenated; concat_examples passes it through (see build_updater)."""
+
+    def __init__(self, x, t):
+        super(PreStacked, self).__init__()
+        self.x, self.t = x, t
+
+    def __len__(self):
+        return self.x.shape[0]
+
+
+def build_updater(batch, seed, use_graph, model="normal"):
+    import torch
+    from mocogan_chainer_b200 import chainer, parallel
+    from mocogan_chainer_b200 import random as mrandom
+    from mocogan_chainer_b200.model import updater as updater_mod
+    from mocogan_chainer_b200.model.net import ImageDiscriminator, ImageGenerator, VideoDiscriminator
+    chainer.config.compute_dtype = "bf16"
+    np.random.seed(0)
+    out = 7 if model == "infogan" else 1
+    G = ImageGenerator(50, 10, 6, 3, 64, 16)
+    Di = ImageDiscriminator(3, out, 64, True, 0.2)
+    Dv = VideoDiscriminator(3, out, 64, True, 0.2)
+    opts = {}
+    for name, m in (("image_gen", G), ("image_dis", Di), ("video_dis", Dv)):
+        o = chainer.optimizers.Adam(alpha=2e-4, beta1=5e-5)   # train.py:93-101
+        o.setup(m)
+        o.add_hook(chainer.optimizer.WeightDecay(1e-5), "hook_dec")
+        opts[name] = o
+    parallel.attach(list(opts.values()))
+    mrandom.set_source(mrandom.DeviceRandom(seed=seed, device="cuda", video_length=16))
+    it = PinnedClipIterator(batch, seed)
+
+    def concat(b):
+        return (b.x, b.t) if isinstance(b, PreStacked) else chainer.dataset.concat_examples(b)
+
+    updater_mod.concat_examples = concat
+    up = updater_mod.Updater(model=model, models=(G, Di, Dv), video_length=16, img_size=64, channel=3, dim_zl=6,
+                             tensorboard_writer=None, iterator=it, optimizer=opts, device=torch.cuda.current_device(),
+                             use_graph=use_graph, graph_warmup=2)
+    return up, it
+
+
+def time_conv_layers(K, torch, peaks):
+    """Per-kernel roofline: each tcgen05 convolution launch of the step timed ALONE with CUDA events (burst peak)."""
+    layers = [  # name, N, Cin, Cout, in_sp, k, s, p, calls per step as (fprop, dgrad, wgrad) of the conv geometry
+        ("Dv.dc2", 35, 64, 128, (13, 32, 32), (4, 4, 4), (1, 2, 2), (0, 1, 1), (2, 3, 2)),
+        ("Dv.dc3", 35, 128, 256, (10, 16, 16), (4, 4, 4), (1, 2, 2), (0, 1, 1), (2, 3, 2)),
+        ("Dv.dc4", 35, 256, 512, (7, 8, 8), (4, 4, 4), (1, 2, 2), (0, 1, 1), (2, 3, 2)),
+        ("Di.dc2", 35, 64, 128, (1, 32, 32), (1, 4, 4), (1, 2, 2), (0, 1, 1), (2, 3, 2)),
+        ("Di.dc3", 35, 128, 256, (1, 16, 16), (1, 4, 4), (1, 2, 2), (0, 1, 1), (2, 3, 2)),
+        ("Di.dc4", 35, 256, 512, (1, 8, 8), (1, 4, 4), (1, 2, 2), (0, 1, 1), (2, 3, 2)),
+        # generator deconvs, written as the conv they are the dgrad of: deconv fwd = dgrad, bwd-data = fprop
+        ("G.dc2", 560, 256, 512, (1, 8, 8), (1, 4, 4), (1, 2, 2), (0, 1, 1), (1, 1, 1)),
+        ("G.dc3", 560, 128, 256, (1, 16, 16), (1, 4, 4), (1, 2, 2), (0, 1, 1), (1, 1, 1)),
+        ("G.dc4", 560, 64, 128, (1, 32, 32), (1, 4, 4), (1, 2, 2), (0, 1, 1), (1, 1, 1)),
+    ]
+    rows = []
+    for name, N, Cin, Cout, in_sp, k, s, p, calls in layers:
+        g = K.make_geom(N, Cin, Cout, in_sp, k, s, p)
+        x = torch.randn((N,) + in_sp + (Cin,), device="cuda").bfloat16()
+        w = (torch.randn((Cout,) + k + (Cin,), device="cuda") * 0.05).bfloat16()
+        gy = torch.randn((N, g.To, g.Ho, g.Wo, Cout), device="cuda").bfloat16()
+        y, dx = torch.empty_like(gy), torch.empty_like(x)
+        dw = torch.zeros(w.shape, device="cuda")
+        flops = 2.0 * N * g.To * g.Ho * g.Wo * Cout * Cin * k[0] * k[1] * k[2]
+        fns = (("fprop", lambda: K.conv_fprop(g, x, w, None, y, K.IMPL_TC)),
+               ("dgrad", lambda: K.conv_dgrad(g, gy, w, None, dx, K.IMPL_TC)),
+               ("wgrad", lambda: K.conv_wgrad(g, x, gy, dw, K.IMPL_TC)))
+        for (kind, fn), ncalls in zip(fns, calls):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            rows.append({"kernel": "tc_conv_%s" % kind, "layer": name, "ms": ms, "gflop": flops / 1e9,
+                         "tflops": flops / ms / 1e9, "calls_per_step": ncalls,
+                         "frac_of_burst_peak": flops / ms / 1e9 / peaks["bf16_burst"]})
+    return rows
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mocogan_chainer_b200 import kernels as K
+    from mocogan_chainer_b200 import parallel
+    rank, world = parallel.init_from_env()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    peaks = load_peaks()
+    K.lib()
+    up, it = build_updater(BATCH, parallel.shard_seed(1234, rank), use_graph=not args.no_graph)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed: inputs resident in HBM, K steps bracketed by barrier + synchronize, max over ranks
+    x_dev = it.x[0].cuda()
+    t_dev = it.t[0].cuda()
+    launches0 = K.launch_count()
+    up.step_host_inputs(x_dev, t_dev)      # first eager step: count our kernel launches per step
+    launches_per_step = K.launch_count() - launches0
+    for _ in range(max(args.warmup, 3) + 2):
+        up.step_host_inputs(x_dev, t_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        up.step_host_inputs(x_dev, t_dev)
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    # ---- end to end through the public API: Updater.update() with pinned host batches, losses read back each step
+    for _ in range(2):
+        up.update()
+    barrier()
+    t0 = time.perf_counter()
+    loss_sink = 0.0
+    for _ in range(args.steps):
+        up.update()
+        loss_sink += sum(float(v) for v in up.losses.values())   # D2H of the step's three losses (synchronises)
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(tt[0]), float(tt[1])
+    assert K.tc_error_flag() == 0, "a tcgen05 kernel reported an mbarrier timeout"
+    assert np.isfinite(loss_sink), "non-finite loss"
+
+    layer_rows, dominant, cpu = None, None, None
+    if rank == 0:
+        layer_rows = time_conv_layers(K, torch, peaks)
+        tot = {}
+        for r in layer_rows:
+            tot[(r["kernel"], r["layer"])] = r["ms"] * r["calls_per_step"]
+        dk = max(tot, key=tot.get)
+        dominant = [r for r in layer_rows if (r["kernel"], r["layer"]) == dk][0]
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_config1()
+    if rank != 0:
+        return
+    steps_per_s = world * args.steps / (ms_dev / 1e3)
+    e2e_steps_per_s = world * args.steps / (ms_e2e / 1e3)
+    conv_ms = sum(r["ms"] * r["calls_per_step"] for r in layer_rows)
+    line = {
+        "metric": "MoCoGAN train steps/s (bs35, 16x3x64x64)", "value": steps_per_s,
+        "unit": "steps/s (batch-35 update_core steps, summed over ranks)", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3) + 3, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2: MoCoGAN normal model (train.py MUG wiring), clips (35,3,16,64,64) "
+                               "per GPU, one update_core (G+Di+Dv) per step" + ("; data-parallel, NCCL all-reduce of the "
+                               "three flat gradient buffers" if world > 1 else ""),
+                   "global_batch": BATCH * world, "parallelism": "dp%d" % world, "cuda_graph": up._graph is not None,
+                   "l2": "no explicit flush: one step streams > 1 GB of activations/weights, >> 126 MB L2",
+                   "weights": "random init (GlorotNormal/LeCunNormal)", "noise": "device Philox"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_steps_per_s, "unit": "steps/s", "h2d_bytes_per_step": int(it.x[0].numel() * 4 + it.t[0].numel() * 4),
+                "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "roofline": {"bound": "tensor", "kernel": dominant["kernel"], "layer": dominant["layer"],
+                     "achieved": dominant["tflops"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                     "frac": dominant["frac_of_burst_peak"], "traffic": None, "peak_source": peaks["src"] + " (burst: kernel timed alone)",
+                     "step": {"useful_gflop": USEFUL_GF_PER_STEP, "achieved_tflops": USEFUL_GF_PER_STEP * steps_per_s / world / 1e3,
+                              "peak_sustained": peaks["bf16_sustained"],
+                              "frac": USEFUL_GF_PER_STEP * steps_per_s / world / 1e3 / peaks["bf16_sustained"],
+                              "tc_conv_ms_per_step_isolated": conv_ms},
+                     "layers": layer_rows},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+def oracle_step_time(config, batch, n_steps, as_executed=True, seed=0):
+    """Times the NumPy restatement of the reference's CPU step (im2col + BLAS, float32, three full backward passes)."""
+    from oracle import mocogan_ref as ref
+    model, G, Di, Dv = ref.build_models(config, dtype=np.float32, seed=seed)
+    up = ref.Updater(model, G, Di, Dv)
+    C = G.out_channels
+    x = np.random.default_rng(1234).uniform(-1, 1, size=(batch, C, 16, 64, 64)).astype(np.float32)
+    t_real = np.random.default_rng(5).integers(0, 6, size=batch) if G.dim_zl else None
+    times = []
+    for i in range(n_steps + 1):
+        t0 = time.perf_counter()
+        # float64 randn then cast, as add_noise does (net.py:13); drawing is part of the reference's step
+        r = ref.draw_step_randoms(np.random.default_rng(100 + i), np.random.default_rng(200 + i), G, Di, Dv, batch, x.shape,
+                                  dtype=np.float32)
+        up.update_core(x, t_real, r, as_executed=as_executed)
+        times.append(time.perf_counter() - t0)
+    return times[1:] if n_steps > 0 else times
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+        return int(n)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline_config1():
+    """BASELINE config 1 (the reference's own CPU-runnable case): batch 8, (16,1,64,64), one as-executed step."""
+    times = oracle_step_time("mnist_normal", 8, 1, as_executed=True)
+    s = float(np.median(times))
+    return {"value": 1.0 / s, "unit": "steps/s (batch-8 update_core steps, config 1)", "cores": cpu_threads(),
+            "kind": "port", "sample": "1 warm-up + 1 timed as-executed update_core of BASELINE config 1 (batch 8, "
+            "clips (16,1,64,64), float32 NumPy/BLAS restatement of the Chainer v3.1.0 CPU path; %.1f s)" % s,
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path on the host cores (oracle port — genuine Chainer
+    3.1.0 cannot be imported here).  Each step is a bounded sample of the workload: `sample_batch`
+    clips of the 35, extrapolated linearly to batch 35."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_batch = 2
+    t_probe = oracle_step_time("mug_normal", sample_batch, 0, as_executed=True)[0]   # doubles as warm-up
+    budget = 200.0
+    n = max(1, min(args.steps, int(budget / max(t_probe, 1e-3))))
+    times = oracle_step_time("mug_normal", sample_batch, n, as_executed=True)
+    s = float(np.median(times))
+    v = (sample_batch / float(BATCH)) / s
+    line = {"impl": "reference", "metric": "MoCoGAN train steps/s (bs35, 16x3x64x64)", "value": v,
+            "unit": "steps/s (batch-35 update_core steps, summed over ranks)", "n_gpus": args.gpus, "steps": n,
+            "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config 2: MoCoGAN normal model (train.py MUG wiring), clips (35,3,16,64,64), "
+                                   "one as-executed update_core per step, CPU"},
+            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cpu_threads(), "kind": "port",
+                             "sample": "%d timed steps at batch %d of 35 (%.2f s each), scaled by %d/35; float32 NumPy/BLAS "
+                                       "restatement of the Chainer v3.1.0 CPU path incl. its discarded backward work"
+                                       % (n, sample_batch, s, sample_batch), "host_cpus": os.cpu_count()},
+            "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

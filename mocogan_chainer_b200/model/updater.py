@@ -109,17 +109,28 @@ class Updater(chainer.training.StandardUpdater):
         ## real data  (updater.py:87-92)
         batch = self.get_iterator('main').next()
         x_real, t_real = concat_examples(batch)
+        if t_real is not None and not torch.is_tensor(t_real):
+            t_real = np.asarray(t_real).astype(np.int32)
+        if self.use_graph:
+            return self.step_host_inputs(x_real, t_real)
         x_real = self.converter(x_real, self.device)
-        if t_real is not None:
-            t_real = self.converter(np.asarray(t_real).astype(np.int32), self.device)
-        self.step_host_inputs(x_real, t_real)
+        t_real = None if t_real is None else self.converter(t_real, self.device)
+        self.step_on_device(x_real, t_real)
 
     def step_host_inputs(self, x_real, t_real):
+        """CUDA-graph path: the batch (host or device) is copied straight into static device buffers, the device part
+        of the step is captured once (after `graph_warmup` eager steps) and replayed afterwards."""
         if not self.use_graph:
+            x_real = self.converter(x_real, self.device)
+            t_real = None if t_real is None else self.converter(t_real, self.device)
             return self.step_on_device(x_real, t_real)
-        # ---- CUDA-graph path: static input buffers, capture once, replay afterwards
+        as_t = lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+        x_real = as_t(x_real)
+        t_real = None if t_real is None else as_t(t_real)
         if self._static is None:
-            self._static = (torch.empty_like(x_real), None if t_real is None else torch.empty_like(t_real))
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self._static = (torch.empty(x_real.shape, dtype=x_real.dtype, device=dev),
+                            None if t_real is None else torch.empty(t_real.shape, dtype=torch.int32, device=dev))
         sx, st = self._static
         sx.copy_(x_real, non_blocking=True)
         if st is not None:
