@@ -130,13 +130,29 @@ static int launch_colreduce(F f, const void* p0, const void* p1, long long M, in
   return 0;
 }
 
-__global__ void bn_stats_finalize(const float* partial, int nblk, int C, double M, const float* gamma,
-                                  const float* beta, float eps, float decay, float* mean, float* invstd,
-                                  float* scale, float* shift, float* avg_mean, float* avg_var) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per channel: lanes stride over the per-block partials, then a shuffle tree (fixed order: deterministic).
+__device__ __forceinline__ void warp_sum_partials(const float* partial, int nblk, int C, int c, double& s, double& q) {
+  const int lane = threadIdx.x & 31;
+  s = 0;
+  q = 0;
+  for (int b = lane; b < nblk; b += 32) {
+    s += partial[(size_t)b * 2 * C + c];
+    q += partial[(size_t)b * 2 * C + C + c];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+}
+__global__ void __launch_bounds__(256) bn_stats_finalize(const float* partial, int nblk, int C, double M,
+                                                         const float* gamma, const float* beta, float eps, float decay,
+                                                         float* mean, float* invstd, float* scale, float* shift,
+                                                         float* avg_mean, float* avg_var) {
+  int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
-  double s = 0, q = 0;
-  for (int b = 0; b < nblk; ++b) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
+  double s, q;
+  warp_sum_partials(partial, nblk, C, c, s, q);
+  if (threadIdx.x & 31) return;
   double mu = s / M;
   double var = q / M - mu * mu;
   if (var < 0) var = 0;
@@ -153,12 +169,13 @@ __global__ void bn_stats_finalize(const float* partial, int nblk, int C, double 
     avg_var[c] = decay * avg_var[c] + (1.f - decay) * (float)(adjust * (var + (double)eps));
   }
 }
-__global__ void sum2_finalize(const float* partial, int nblk, int C, float* out_a, float* out_b, int accumulate,
-                              float* acc_a = nullptr, float* acc_b = nullptr) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) sum2_finalize(const float* partial, int nblk, int C, float* out_a, float* out_b,
+                                                     int accumulate, float* acc_a = nullptr, float* acc_b = nullptr) {
+  int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
-  double s = 0, q = 0;
-  for (int b = 0; b < nblk; ++b) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
+  double s, q;
+  warp_sum_partials(partial, nblk, C, c, s, q);
+  if (threadIdx.x & 31) return;
   if (out_a) out_a[c] = (accumulate ? out_a[c] : 0.f) + (float)s;
   if (out_b) out_b[c] = (accumulate ? out_b[c] : 0.f) + (float)q;
   if (acc_a) acc_a[c] += (float)s;
@@ -405,7 +422,7 @@ int mcg_bn_stats(const void* y, long long M, int C, int dtype, const float* gamm
   int rc = launch_colreduce(StatsF{}, y, nullptr, M, C, dtype, workspace, workspace_bytes, as_stream(stream), &nblk,
                             "mcg_bn_stats");
   if (rc) return rc;
-  bn_stats_finalize<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>((const float*)workspace, nblk, C, (double)M, gamma,
+  bn_stats_finalize<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>((const float*)workspace, nblk, C, (double)M, gamma,
                                                                     beta, eps, decay, mean, invstd, scale, shift,
                                                                     avg_mean, avg_var);
   MCG_CHECK_LAUNCH("mcg_bn_stats(finalize)");
@@ -419,7 +436,7 @@ int mcg_colsum(const void* g, long long M, int C, int dtype, float* out, int acc
   int rc = launch_colreduce(SumF{}, g, nullptr, M, C, dtype, workspace, workspace_bytes, as_stream(stream), &nblk,
                             "mcg_colsum");
   if (rc) return rc;
-  sum2_finalize<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>((const float*)workspace, nblk, C, out, nullptr,
+  sum2_finalize<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>((const float*)workspace, nblk, C, out, nullptr,
                                                                 accumulate);
   MCG_CHECK_LAUNCH("mcg_colsum(finalize)");
   return 0;
@@ -438,7 +455,7 @@ int mcg_act_bn_bwd_reduce(const void* g, const void* y, long long M, int C, int 
   if (rc) return rc;
   // partial[.,0,:] = sum g' -> dbeta ; partial[.,1,:] = sum g' xhat -> dgamma; acc_* are the parameter
   // gradients, which accumulate across the real and fake calls of one pass as in Chainer.
-  sum2_finalize<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>((const float*)workspace, nblk, C, dbeta, dgamma, 0,
+  sum2_finalize<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>((const float*)workspace, nblk, C, dbeta, dgamma, 0,
                                                                 acc_dbeta, acc_dgamma);
   MCG_CHECK_LAUNCH("mcg_act_bn_bwd_reduce(finalize)");
   return 0;

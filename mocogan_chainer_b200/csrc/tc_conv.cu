@@ -19,7 +19,7 @@
 
 namespace mcg {
 
-enum { kFprop = 0, kDgrad = 1, kWgrad = 2 };
+enum { kFprop = 0, kDgrad = 1, kWgrad = 2, kDgradSmall = 3 };  // kDgradSmall: dgrad with <= 16 input channels
 
 struct TcTap {
   int16_t dw, dh, dt, kidx;  // A-box coordinate offsets; kidx = linear tap index (kt,kh,kw)
@@ -37,6 +37,7 @@ struct TcParams {
   int Cin, Cout, Ktot;                                        // Ktot = taps*Cin (row length of w / dw)
   int tap_begin[8], tap_count[8];
   int total_boxes, boxes_per_split;                           // wgrad
+  int total_slabs, kreal;                                     // wgrad: valid 64-row slabs; real row length of dw
   int out_f32;
   TcTap taps[64];
 };
@@ -67,7 +68,8 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
   }
-  if (warp == 1) { tmem_alloc(&tmem_slot, BN); tmem_relinquish(); }
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  if (warp == 1) { tmem_alloc(&tmem_slot, TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -113,6 +115,8 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
                       h0 * P.a_mul_h + P.a_add_h + tp.dh, t0 * P.a_mul_t + P.a_add_t + tp.dt, n0);
           if (MODE == kFprop) {
             tma_load_2d(b_dst, &mapB, &full_bar[s], tp.kidx * P.Cin + c * 64, ncol0);
+          } else if (MODE == kDgradSmall) {  // transposed weights (16 padded ci rows) x (taps*Cout), K-major
+            tma_load_2d(b_dst, &mapB, &full_bar[s], tp.kidx * P.Cout + c * 64, 0);
           } else {
 #pragma unroll
             for (int sl = 0; sl < BN / 64; ++sl)
@@ -128,8 +132,9 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
 #pragma unroll
           for (int sl = 0; sl < 2; ++sl) {
             const int u = u0 + sl;
-            const TcTap tp = P.taps[u / P.chunks];
-            tma_load_5d(a_dst + sl * 8192, &mapA, &full_bar[s], (u % P.chunks) * 64, pw0 * P.a_mul_w + P.a_add_w + tp.dw,
+            const bool live = u < P.total_slabs;  // an odd slab count leaves one dummy slab: channel coordinate out of
+            const TcTap tp = P.taps[live ? u / P.chunks : 0];  // bounds -> TMA zero-fills it
+            tma_load_5d(a_dst + sl * 8192, &mapA, &full_bar[s], live ? (u % P.chunks) * 64 : P.Cin, pw0 * P.a_mul_w + P.a_add_w + tp.dw,
                         ph0 * P.a_mul_h + P.a_add_h + tp.dh, pt0 * P.a_mul_t + P.a_add_t + tp.dt, pn0);
           }
 #pragma unroll
@@ -141,7 +146,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
   } else if (warp == 1) {
     // ================================================= MMA issuer ===========================================
     if (lane == 0) {
-      constexpr int A_MN = (MODE == kWgrad), B_MN = (MODE != kFprop);
+      constexpr int A_MN = (MODE == kWgrad), B_MN = (MODE == kDgrad || MODE == kWgrad);
       const uint32_t idesc = make_idesc_bf16(128, BN, A_MN, B_MN);
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % STAGES;
@@ -177,6 +182,18 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
         const int on = n0 + ib;
         const bool valid = ow < P.full_w && oh < P.full_h && ot < P.full_t && on < P.EN;
         const long long base = (long long)on * P.os_n + (long long)ot * P.os_t + (long long)oh * P.os_h + (long long)ow * P.os_w + ncol0;
+        if (MODE == kDgradSmall) {
+          uint32_t v[16];
+          tmem_ld16(tmem + (uint32_t(q * 32) << 16), v);
+          tmem_ld_wait();
+          if (valid) {
+            for (int i = 0; i < P.Cin; ++i) {
+              const float f = __uint_as_float(v[i]) + (bias ? bias[i] : 0.f);
+              if (P.out_f32) reinterpret_cast<float*>(out)[base + i] = f;
+              else reinterpret_cast<__nv_bfloat16*>(out)[base + i] = __float2bfloat16_rn(f);
+            }
+          }
+        } else
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
@@ -207,23 +224,27 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
         }
       } else {
         const int u = blockIdx.x * 2 + (r >> 6);
-        const TcTap tp = P.taps[u / P.chunks];
+        const bool live = u < P.total_slabs;
+        const TcTap tp = P.taps[live ? u / P.chunks : 0];
         const long long kidx = (long long)tp.kidx * P.Cin + (u % P.chunks) * 64 + (r & 63);
+        const bool row_ok = live && kidx < P.kreal;
         float* dw = reinterpret_cast<float*>(out);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem + (uint32_t(q * 32) << 16) + c0, v);
           tmem_ld_wait();
+          if (row_ok) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(dw + (long long)(ncol0 + c0 + i) * P.Ktot + kidx, __uint_as_float(v[i]));
+            for (int i = 0; i < 32; ++i) atomicAdd(dw + (long long)(ncol0 + c0 + i) * P.kreal + kidx, __uint_as_float(v[i]));
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, BN);
+  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // =============================================================================================================
@@ -327,7 +348,7 @@ template <int MODE, int BN>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, dim3 grid, void* out, const float* bias,
                      cudaStream_t st, const char* who) {
   constexpr int STAGE = A_BYTES + BN * 128;
-  constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);  // BN<=128: ~96 KB so two CTAs share an SM
+  constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : (BN == 64 ? 4 : 6));  // BN<=128: ~96 KB so two CTAs share an SM
   size_t smem = (size_t)STAGES * STAGE + 1024;
   static bool configured = false;
   if (!configured) {
@@ -359,7 +380,7 @@ bool tc_supported(const mcg_conv_geom* g) {
 }
 
 int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void* out, const float* bias, int out_dtype,
-            cudaStream_t st) {
+            cudaStream_t st, int kreal = 0) {
   const char* who = mode == kFprop ? "mcg_conv_fprop(tc)" : mode == kDgrad ? "mcg_conv_dgrad(tc)" : "mcg_conv_wgrad(tc)";
   if (!tc_supported(g)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: needs Cin,Cout %% 64 == 0, stride <= 2, <= 64 taps", who);
   TcParams P;
@@ -447,8 +468,9 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
       for (int kh = 0; kh < g->kH; ++kh)
         for (int kw = 0; kw < g->kW; ++kw, ++j) P.taps[j] = TcTap{(int16_t)kw, (int16_t)kh, (int16_t)kt, (int16_t)j};
     const int slabs = taps * P.chunks;
-    if (slabs % 2) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: taps*Cin/64 must be even", who);
-    const int mtiles = slabs / 2;
+    const int mtiles = (slabs + 1) / 2;   // an odd count leaves one zero-filled dummy slab in the last tile
+    P.total_slabs = slabs;
+    P.kreal = kreal > 0 ? kreal : P.Ktot;
     int bn = 64;
     for (int c = 256; c >= 64; c /= 2)
       if (g->Cout % c == 0) { bn = c; break; }
@@ -467,6 +489,151 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
   }
 }
 
+
+// =============================================================================================================
+// 3-channel image layers (Di.dc1, Dv.dc1, G.dc5): Cin < 64 cannot feed a 16-byte-aligned TMA box, so
+//   fprop / wgrad : x is expanded once into an explicit im2col matrix cols[M][Kp] (Kp = taps*Cin rounded up to 64) in
+//                   caller workspace and the layer becomes a plain GEMM = a 1x1 "convolution" over a 1-D line of M
+//                   pixels through the same tcgen05 kernel;
+//   dgrad         : output has Cin <= 16 channels -> kDgradSmall (N = 16 MMA, transposed zero-padded weights).
+// These layers are HBM/L2-bound (Dv.dc1 writes 29.8 M outputs, G.dc5 reads 36.7 M inputs), not tensor-bound.
+// =============================================================================================================
+__global__ void __launch_bounds__(256) im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ cols,
+                                                     long long M, int Kp, int Cin, int Ti, int Hi, int Wi, int To, int Ho,
+                                                     int Wo, int kT, int kH, int kW, int sT, int sH, int sW, int pT, int pH,
+                                                     int pW) {
+  const int groups = Kp / 8;
+  const int K = kT * kH * kW * Cin;
+  const long long total = M * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / groups;
+    const int k0 = (int)(idx % groups) * 8;
+    int wo = (int)(m % Wo); long long r = m / Wo;
+    int ho = (int)(r % Ho); r /= Ho;
+    int to = (int)(r % To); const long long n = r / To;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = k0 + i;
+      float val = 0.f;
+      if (k < K) {
+        const int tap = k / Cin, ci = k - tap * Cin;
+        const int kw = tap % kW, kh = (tap / kW) % kH, kt = tap / (kW * kH);
+        const int ti = to * sT - pT + kt, hi = ho * sH - pH + kh, wi = wo * sW - pW + kw;
+        if ((unsigned)ti < (unsigned)Ti && (unsigned)hi < (unsigned)Hi && (unsigned)wi < (unsigned)Wi)
+          val = __bfloat162float(x[((((long long)n * Ti + ti) * Hi + hi) * Wi + wi) * Cin + ci]);
+      }
+      v[i] = __float2bfloat16_rn(val);
+    }
+    *reinterpret_cast<uint4*>(cols + m * Kp + k0) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+// wp[co][Kp] = w[co][k] (k < K) else 0
+__global__ void pad_rows_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wp, int rows, int K, int Kp) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * Kp; i += gridDim.x * blockDim.x) {
+    const int r = i / Kp, k = i % Kp;
+    wp[i] = k < K ? w[(long long)r * K + k] : __float2bfloat16_rn(0.f);
+  }
+}
+// wt[ci (16 rows, zero-padded)][tap*Cout + co] = w[co][tap][ci]
+__global__ void transpose_small_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wt, int Cout, int taps,
+                                       int Cin) {
+  const int cols = taps * Cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 16 * cols; i += gridDim.x * blockDim.x) {
+    const int ci = i / cols, rem = i % cols, tap = rem / Cout, co = rem % Cout;
+    wt[i] = ci < Cin ? w[((long long)co * taps + tap) * Cin + ci] : __float2bfloat16_rn(0.f);
+  }
+}
+
+static long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
+
+bool tc_small_supported(const mcg_conv_geom* g) {
+  return g->Cin <= 16 && g->Cout % 64 == 0 && g->sT <= 2 && g->sH <= 2 && g->sW <= 2 && g->kT * g->kH * g->kW <= 64;
+}
+size_t tc_small_workspace(const mcg_conv_geom* g) {
+  const long long M = (long long)g->N * g->To * g->Ho * g->Wo;
+  const long long K = (long long)g->kT * g->kH * g->kW * g->Cin, Kp = round_up(K, 64);
+  return (size_t)(M * Kp * 2 + round_up((long long)g->Cout * Kp * 2, 1024) + round_up(16LL * g->kT * g->kH * g->kW * g->Cout * 2, 1024) + 4096);
+}
+
+int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b, void* out, const float* bias, int out_dtype,
+                  void* ws, size_t ws_bytes, cudaStream_t st) {
+  const char* who = mode == kFprop ? "mcg_conv_fprop(tc,small-C)" : mode == kDgrad ? "mcg_conv_dgrad(tc,small-C)" : "mcg_conv_wgrad(tc,small-C)";
+  if (!tc_small_supported(g)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: needs Cin <= 16, Cout %% 64 == 0", who);
+  const int taps = g->kT * g->kH * g->kW;
+  const long long M = (long long)g->N * g->To * g->Ho * g->Wo;
+  const int K = taps * g->Cin, Kp = (int)round_up(K, 64);
+  if (!ws || ws_bytes < tc_small_workspace(g)) MCG_FAIL(MCG_ERR_WORKSPACE, "%s: workspace %zu < %zu", who, ws_bytes, tc_small_workspace(g));
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+  __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* wpad = reinterpret_cast<__nv_bfloat16*>(base + round_up(M * Kp * 2, 1024));
+  int rc;
+  if (mode == kDgrad) {
+    // a = dy (N,To,Ho,Wo,Cout), b = w bf16 (Cout,taps,Cin), out = dx (N,Ti,Hi,Wi,Cin)
+    __nv_bfloat16* wt = wpad;
+    transpose_small_kernel<<<64, 256, 0, st>>>((const __nv_bfloat16*)b, wt, g->Cout, taps, g->Cin);
+    MCG_CHECK_LAUNCH(who);
+    TcParams P;
+    memset(&P, 0, sizeof(P));
+    P.Cin = g->Cin; P.Cout = g->Cout; P.Ktot = K;
+    P.out_f32 = (out_dtype == MCG_F32);
+    const int cw = g->sW, ch = g->sH, ct = g->sT;
+    const int EW = ceil_div(g->Wi, cw), EH = ceil_div(g->Hi, ch), ET = ceil_div(g->Ti, ct);
+    Box bx = choose_box(128, EW, EH, ET, g->N);
+    P.BW = bx.w; P.BH = bx.h; P.BT = bx.t; P.BB = bx.b;
+    P.nbw = ceil_div(EW, bx.w); P.nbh = ceil_div(EH, bx.h); P.nbt = ceil_div(ET, bx.t); P.nbb = ceil_div(g->N, bx.b);
+    P.EW = EW; P.EH = EH; P.ET = ET; P.EN = g->N;
+    P.full_w = g->Wi; P.full_h = g->Hi; P.full_t = g->Ti;
+    P.a_mul_w = P.a_mul_h = P.a_mul_t = 1;
+    P.o_mul_w = cw; P.o_mul_h = ch; P.o_mul_t = ct;
+    P.cls_w = cw; P.cls_h = ch; P.cls_t = ct;
+    P.os_w = g->Cin; P.os_h = (long long)g->Wi * g->Cin; P.os_t = (long long)g->Hi * P.os_h; P.os_n = (long long)g->Ti * P.os_t;
+    P.chunks = g->Cout / 64;
+    int ncls = cw * ch * ct, j = 0;
+    for (int c = 0; c < ncls; ++c) {
+      const int pw = c % cw, ph = (c / cw) % ch, pt = c / (cw * ch);
+      P.tap_begin[c] = j;
+      for (int kt = 0; kt < g->kT; ++kt) {
+        if ((pt + g->pT - kt) % ct) continue;
+        for (int kh = 0; kh < g->kH; ++kh) {
+          if ((ph + g->pH - kh) % ch) continue;
+          for (int kw = 0; kw < g->kW; ++kw) {
+            if ((pw + g->pW - kw) % cw) continue;
+            P.taps[j++] = TcTap{(int16_t)((pw + g->pW - kw) / cw), (int16_t)((ph + g->pH - kh) / ch),
+                                (int16_t)((pt + g->pT - kt) / ct), (int16_t)((kt * g->kH + kh) * g->kW + kw)};
+          }
+        }
+      }
+      P.tap_count[c] = j - P.tap_begin[c];
+    }
+    CUtensorMap ma, mb;
+    if ((rc = act_map(&ma, a, g->Cout, g->Wo, g->Ho, g->To, g->N, bx.w, bx.h, bx.t, bx.b, 1, 1, 1))) return rc;
+    uint64_t d2[2] = {(uint64_t)taps * g->Cout, 16}, s2[1] = {(uint64_t)taps * g->Cout * 2};
+    uint32_t b2[2] = {64, 16}, e2[2] = {1, 1};
+    if ((rc = get_map(&mb, wt, 2, d2, s2, b2, e2))) return rc;
+    long long mt = (long long)P.nbw * P.nbh * P.nbt * P.nbb * ncls;
+    dim3 grid((unsigned)mt, 1, 1);
+    return launch_tc<kDgradSmall, 16>(ma, mb, P, grid, out, bias, st, who);
+  }
+  // fprop / wgrad: im2col, then a GEMM over a 1-D line of M pixels with Kp channels
+  const void* x = a;
+  im2col_kernel<<<num_sms() * 16, 256, 0, st>>>((const __nv_bfloat16*)x, cols, M, Kp, g->Cin, g->Ti, g->Hi, g->Wi, g->To, g->Ho,
+                                                 g->Wo, g->kT, g->kH, g->kW, g->sT, g->sH, g->sW, g->pT, g->pH, g->pW);
+  MCG_CHECK_LAUNCH(who);
+  if (M > 0x7fffffffLL) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: too many pixels", who);
+  mcg_conv_geom g2 = {1, Kp, g->Cout, 1, 1, (int)M, 1, 1, (int)M, 1, 1, 1, 1, 1, 1, 0, 0, 0};
+  if (mode == kFprop) {
+    const void* wk = b;
+    if (Kp != K) {
+      pad_rows_kernel<<<32, 256, 0, st>>>((const __nv_bfloat16*)b, wpad, g->Cout, K, Kp);
+      MCG_CHECK_LAUNCH(who);
+      wk = wpad;
+    }
+    return tc_conv(kFprop, &g2, cols, wk, out, bias, out_dtype, st);
+  }
+  return tc_conv(kWgrad, &g2, cols, b, out, nullptr, MCG_F32, st, K);
+}
+
 }  // namespace mcg
 
 using namespace mcg;
@@ -478,16 +645,17 @@ int simt_conv(int mode, const mcg_conv_geom* c, const void* a, const void* b_act
 extern "C" {
 
 size_t mcg_conv_workspace_bytes(const mcg_conv_geom* g, int impl) {
-  (void)g; (void)impl;
+  if (g && impl == MCG_IMPL_TC && !tc_supported(g) && tc_small_supported(g)) return tc_small_workspace(g);
   return 0;
 }
 
 int mcg_conv_fprop(const mcg_conv_geom* g, const void* x, const void* w, const float* bias, void* y, int dtype,
                    int out_dtype, int impl, void* workspace, size_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
   if (!g || !x || !w || !y) MCG_FAIL(MCG_ERR_SHAPE, "mcg_conv_fprop: null pointer");
   if (impl == MCG_IMPL_TC) {
     if (dtype != MCG_BF16) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_fprop(tc): activations must be bf16");
+    if (!tc_supported(g) && tc_small_supported(g))
+      return tc_conv_small(0, g, x, w, y, bias, out_dtype, workspace, workspace_bytes, as_stream(stream));
     return tc_conv(0, g, x, w, y, bias, out_dtype, as_stream(stream));
   }
   return simt_conv(0, g, x, nullptr, (const float*)w, bias, y, dtype, out_dtype, 0, as_stream(stream));
@@ -495,11 +663,12 @@ int mcg_conv_fprop(const mcg_conv_geom* g, const void* x, const void* w, const f
 
 int mcg_conv_dgrad(const mcg_conv_geom* g, const void* dy, const void* w, const float* bias, void* dx, int dtype,
                    int out_dtype, int accumulate, int impl, void* workspace, size_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
   if (!g || !dy || !w || !dx) MCG_FAIL(MCG_ERR_SHAPE, "mcg_conv_dgrad: null pointer");
   if (impl == MCG_IMPL_TC) {
     if (dtype != MCG_BF16) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_dgrad(tc): activations must be bf16");
     if (accumulate) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_dgrad(tc): accumulate not supported");
+    if (!tc_supported(g) && tc_small_supported(g))
+      return tc_conv_small(1, g, dy, w, dx, bias, out_dtype, workspace, workspace_bytes, as_stream(stream));
     return tc_conv(1, g, dy, w, dx, bias, out_dtype, as_stream(stream));
   }
   return simt_conv(1, g, dy, nullptr, (const float*)w, bias, dx, dtype, out_dtype, accumulate, as_stream(stream));
@@ -507,10 +676,11 @@ int mcg_conv_dgrad(const mcg_conv_geom* g, const void* dy, const void* w, const 
 
 int mcg_conv_wgrad(const mcg_conv_geom* g, const void* x, const void* dy, float* dw, int dtype, int impl, void* workspace,
                    size_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
   if (!g || !x || !dy || !dw) MCG_FAIL(MCG_ERR_SHAPE, "mcg_conv_wgrad: null pointer");
   if (impl == MCG_IMPL_TC) {
     if (dtype != MCG_BF16) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_wgrad(tc): activations must be bf16");
+    if (!tc_supported(g) && tc_small_supported(g))
+      return tc_conv_small(2, g, x, dy, dw, nullptr, MCG_F32, workspace, workspace_bytes, as_stream(stream));
     return tc_conv(2, g, x, dy, dw, nullptr, MCG_F32, as_stream(stream));
   }
   return simt_conv(2, g, dy, x, nullptr, nullptr, dw, dtype, MCG_F32, 1, as_stream(stream));

@@ -59,25 +59,39 @@ def workspace(nbytes, device):
 
 
 def tc_ok(g):
+    """Shapes the tcgen05 path takes: 64-multiple channels (implicit GEMM) or <= 16 input channels (im2col GEMM /
+    narrow-N dgrad for the 3-channel image layers)."""
     if os.environ.get("MCG_DISABLE_TC"):   # debugging aid: route every convolution through the CUDA-core kernel
         return False
-    return (g.Cin % 64 == 0 and g.Cout % 64 == 0 and max(g.sT, g.sH, g.sW) <= 2 and g.kT * g.kH * g.kW <= 64
-            and (g.kT * g.kH * g.kW * (g.Cin // 64)) % 2 == 0)
+    if max(g.sT, g.sH, g.sW) > 2 or g.kT * g.kH * g.kW > 64 or g.Cout % 64:
+        return False
+    return g.Cin % 64 == 0 or g.Cin <= 16
+
+
+def _conv_ws(g, impl, device):
+    nb = lib().mcg_conv_workspace_bytes(C.byref(g), impl)
+    if nb == 0:
+        return None, 0
+    buf = torch.empty(int(nb), dtype=torch.uint8, device=device)
+    return buf, buf.numel()
 
 
 def conv_fprop(g, x, w, bias, y, impl):
-    check(lib().mcg_conv_fprop(C.byref(g), ptr(x), ptr(w), ptr(bias), ptr(y), dt_code(x), dt_code(y), impl, None, 0,
+    ws, nb = _conv_ws(g, impl, x.device)
+    check(lib().mcg_conv_fprop(C.byref(g), ptr(x), ptr(w), ptr(bias), ptr(y), dt_code(x), dt_code(y), impl, ptr(ws), nb,
                                stream()), "mcg_conv_fprop")
 
 
 def conv_dgrad(g, dy, w, bias, dx, impl, accumulate=False):
+    ws, nb = _conv_ws(g, impl, dy.device)
     check(lib().mcg_conv_dgrad(C.byref(g), ptr(dy), ptr(w), ptr(bias), ptr(dx), dt_code(dy), dt_code(dx),
-                               int(accumulate), impl, None, 0, stream()), "mcg_conv_dgrad")
+                               int(accumulate), impl, ptr(ws), nb, stream()), "mcg_conv_dgrad")
 
 
 def conv_wgrad(g, x, dy, dw, impl):
     assert dw.dtype == torch.float32
-    check(lib().mcg_conv_wgrad(C.byref(g), ptr(x), ptr(dy), ptr(dw), dt_code(x), impl, None, 0, stream()),
+    ws, nb = _conv_ws(g, impl, x.device)
+    check(lib().mcg_conv_wgrad(C.byref(g), ptr(x), ptr(dy), ptr(dw), dt_code(x), impl, ptr(ws), nb, stream()),
           "mcg_conv_wgrad")
 
 

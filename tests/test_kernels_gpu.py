@@ -124,6 +124,10 @@ TC_CASES = [
     ("tc3d", 3, 2, 64, 64, (7, 16, 16), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
     ("tc3d_last", 3, 3, 64, 128, (7, 8, 8), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
     ("tc2d_s1", 2, 2, 128, 64, (9, 9), (3, 3), (1, 1), (1, 1)),
+    # 3-channel image layers: im2col GEMM (fprop/wgrad) + narrow-N dgrad
+    ("tc_di_dc1", 2, 3, 3, 64, (16, 16), (4, 4), (2, 2), (1, 1)),
+    ("tc_dv_dc1", 3, 2, 3, 64, (7, 16, 16), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
+    ("tc_c1", 2, 3, 1, 64, (16, 16), (4, 4), (2, 2), (1, 1)),
 ]
 
 
@@ -134,15 +138,17 @@ def test_conv_tcgen05_bf16(K, case):
 
 def test_conv_tc_rejects_unsupported(K):
     from mocogan_chainer_b200._lib import McgError
-    g = K.make_geom(2, 3, 64, (1, 16, 16), (1, 4, 4), (1, 2, 2), (0, 1, 1))
-    x = torch.zeros((2, 1, 16, 16, 3), dtype=torch.bfloat16, device="cuda")
-    w = torch.zeros((64, 1, 4, 4, 3), dtype=torch.bfloat16, device="cuda")
+    g = K.make_geom(2, 24, 64, (1, 16, 16), (1, 4, 4), (1, 2, 2), (0, 1, 1))   # 24 channels: neither path takes it
+    x = torch.zeros((2, 1, 16, 16, 24), dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros((64, 1, 4, 4, 24), dtype=torch.bfloat16, device="cuda")
     y = torch.zeros((2, 1, 8, 8, 64), dtype=torch.bfloat16, device="cuda")
     with pytest.raises(McgError):
         K.conv_fprop(g, x, w, None, y, K.IMPL_TC)
 
 
 FULL_TC = [
+    ("Dv.dc1", 35, 3, 64, (16, 64, 64), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
+    ("G.dc5", 560, 3, 64, (1, 64, 64), (1, 4, 4), (1, 2, 2), (0, 1, 1)),
     ("Dv.dc2", 35, 64, 128, (13, 32, 32), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
     ("Dv.dc3", 35, 128, 256, (10, 16, 16), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
     ("Dv.dc4", 35, 256, 512, (7, 8, 8), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
