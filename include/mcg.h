@@ -28,6 +28,9 @@ extern "C" {
 enum { MCG_F32 = 0, MCG_BF16 = 1 };
 enum { MCG_ACT_NONE = 0, MCG_ACT_RELU = 1, MCG_ACT_LRELU = 2, MCG_ACT_TANH = 3 };
 enum { MCG_IMPL_SIMT = 0, MCG_IMPL_TC = 1 };          /* fp32 CUDA-core path | tcgen05 bf16 path */
+/* OR-ed into `impl` for fprop/wgrad of a layer with Cin <= 16: the workspace already holds this x's im2col matrix
+ * (written by an earlier fprop/wgrad call on the same x and geometry), so it is not rebuilt. */
+#define MCG_FLAG_COLS_VALID 0x100
 enum { MCG_ERR_SHAPE = -1, MCG_ERR_UNSUPPORTED = -2, MCG_ERR_WORKSPACE = -3, MCG_ERR_DRIVER = -4 };
 
 int mcg_version(void);
@@ -52,7 +55,9 @@ typedef struct {
  * wgrad : dw[co,kt,kh,kw,ci] += sum_{n,to,ho,wo} dy[..co] * x[..ci]      (always accumulates, fp32)
  * impl = MCG_IMPL_SIMT: x/dy/dx/y of type `dtype`, w fp32.  impl = MCG_IMPL_TC: activations bf16, w bf16,
  *         requires Cin % 64 == 0 and Cout % 64 == 0 and stride in {1,2}.  out_dtype selects y / dx type.
- * mcg_conv_workspace_bytes: scratch the three calls may need for this geometry (0 today).               */
+ *         Layers with Cin <= 16 (the 3-channel image layers) are also taken: fprop/wgrad through an im2col
+ *         matrix in `workspace`, dgrad through a narrow-N kernel with transposed weights in `workspace`.
+ * mcg_conv_workspace_bytes: scratch the three calls need for this geometry (0 for the implicit-GEMM shapes). */
 size_t mcg_conv_workspace_bytes(const mcg_conv_geom* g, int impl);
 int mcg_conv_fprop(const mcg_conv_geom* g, const void* x, const void* w, const float* bias, void* y, int dtype,
                    int out_dtype, int impl, void* workspace, size_t workspace_bytes, void* stream);

@@ -150,8 +150,11 @@ class ConvolutionND(FunctionNode):
         odt = self.out_dtype or xp.dtype
         y = torch.empty((N,) + out_sp + (Cout,), dtype=odt, device=xp.device)
         bias = None if b is None else b.store
+        self.cols_ws = None
         if not self.deconv:
-            K.conv_fprop(g, xp, w, bias, y, self.impl)
+            ws = K.conv_fprop(g, xp, w, bias, y, self.impl)
+            if config.enable_backprop:
+                self.cols_ws = ws   # small-Cin layers: keep x's im2col matrix for wgrad
         else:
             K.conv_dgrad(g, xp, w, bias, y, self.impl)
         self.xp = xp
@@ -163,18 +166,20 @@ class ConvolutionND(FunctionNode):
         gyp = as_physical(gys[0], self.xp.dtype)
         w = W.bstore if self.impl == K.IMPL_TC else W.store
         gx = None
+        ws = None
         if 0 in idx:
             dx = torch.empty_like(self.xp)
             if not self.deconv:
                 K.conv_dgrad(g, gyp, w, None, dx, self.impl)
             else:
-                K.conv_fprop(g, gyp, w, None, dx, self.impl)
+                ws = K.conv_fprop(g, gyp, w, None, dx, self.impl)
             gx = logical_view(dx, self.nd)
         if 1 in idx:
             if not self.deconv:
-                K.conv_wgrad(g, self.xp, gyp, W.gstore, self.impl)
+                K.conv_wgrad(g, self.xp, gyp, W.gstore, self.impl, ws=self.cols_ws, cols_valid=self.cols_ws is not None)
             else:
-                K.conv_wgrad(g, gyp, self.xp, W.gstore, self.impl)
+                K.conv_wgrad(g, gyp, self.xp, W.gstore, self.impl, ws=ws, cols_valid=ws is not None)
+        self.cols_ws = None
         if 2 in idx and b is not None and self.bias_grad:
             gb_src = as_physical(gys[0])  # original precision: the fp32 loss gradient of the last layer cancels heavily
             M = gb_src.numel() // gb_src.shape[-1]

@@ -3,6 +3,7 @@
 // (3-channel image layers, the 1x1 -> 4x4 first deconvolution, the final dot-product layers).
 // One kernel, three index maps (fprop / dgrad / wgrad) over channels-last activations and (Cout,kT,kH,kW,Cin) weights.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mcg {
 
@@ -140,6 +141,75 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(Geo g, const T* __restri
   }
 }
 
+
+// ---- "full-window" layers: the kernel covers the whole input and the output is 1x1(x1) — Di.dc5, Dv.dc5 and the
+// generator's first deconvolution (net.py:44,137,178).  They are plain GEMMs over contiguous rows:
+//   fprop : y[m][col] = bias[col] + sum_k x[m][k] * w[col][k]          (M = batch, K = taps*Cin)
+//   dgrad : dx[m][k]  = bias[k % Cin] + sum_co dy[m][co] * w[co][k]
+template <typename T>
+__global__ void __launch_bounds__(256) fullwin_fprop_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, void* __restrict__ y,
+                                                            int out_bf16, int M, int Ncols, int K, int cols_per_block) {
+  __shared__ float red[8];
+  const int m = blockIdx.x;
+  const T* xr = x + (long long)m * K;
+  for (int cc = 0; cc < cols_per_block; ++cc) {
+    const int col = blockIdx.y * cols_per_block + cc;
+    if (col >= Ncols) break;
+    const float* wr = w + (long long)col * K;
+    float acc = 0.f;
+    if ((K & 7) == 0) {
+      for (int k = threadIdx.x * 8; k < K; k += 256 * 8) {
+        float xv[8], wv[8];
+        ld8<T>(xr + k, xv);
+        ld8<float>(wr + k, wv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(xv[i], wv[i], acc);
+      }
+    } else {
+      for (int k = threadIdx.x; k < K; k += 256) acc = fmaf(ld<T>(xr, k), wr[k], acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int i = 0; i < 8; ++i) s += red[i];
+      if (bias) s += bias[col];
+      const long long o = (long long)m * Ncols + col;
+      if (out_bf16) reinterpret_cast<__nv_bfloat16*>(y)[o] = __float2bfloat16_rn(s);
+      else reinterpret_cast<float*>(y)[o] = s;
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) fullwin_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, void* __restrict__ dx,
+                                                            int out_bf16, int accumulate, int M, int Cout, int K, int Cin) {
+  const long long total = (long long)M * K;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(idx / K), k = (int)(idx % K);
+    float acc = bias ? bias[k % Cin] : 0.f;
+    for (int co = 0; co < Cout; ++co) acc = fmaf(ld<T>(dy, (long long)m * Cout + co), w[(long long)co * K + k], acc);
+    if (out_bf16) {
+      __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(dx);
+      if (accumulate) acc += __bfloat162float(p[idx]);
+      p[idx] = __float2bfloat16_rn(acc);
+    } else {
+      float* p = reinterpret_cast<float*>(dx);
+      if (accumulate) acc += p[idx];
+      p[idx] = acc;
+    }
+  }
+}
+
+static bool is_full_window(const Geo& g) {
+  return g.To == 1 && g.Ho == 1 && g.Wo == 1 && g.pT == 0 && g.pH == 0 && g.pW == 0 && g.kT == g.Ti && g.kH == g.Hi &&
+         g.kW == g.Wi;
+}
+
 static int make_geo(const mcg_conv_geom* c, Geo* g, const char* who) {
   if (!c) MCG_FAIL(MCG_ERR_SHAPE, "%s: null geometry", who);
   *g = Geo{c->N, c->Cin, c->Cout, c->Ti, c->Hi, c->Wi, c->To, c->Ho, c->Wo, c->kT, c->kH, c->kW,
@@ -165,6 +235,24 @@ int simt_conv(int mode, const mcg_conv_geom* c, const void* a, const void* b_act
   const char* who = mode == kFprop ? "mcg_conv_fprop(simt)" : mode == kDgrad ? "mcg_conv_dgrad(simt)" : "mcg_conv_wgrad(simt)";
   if (int rc = make_geo(c, &g, who)) return rc;
   if (dtype != MCG_F32 && dtype != MCG_BF16) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: dtype %d", who, dtype);
+  static const bool no_fullwin = getenv("MCG_NO_FULLWIN") != nullptr;  // debugging aid
+  if (!no_fullwin && is_full_window(g) && mode != kWgrad) {
+    const int ob = out_dtype == MCG_BF16;
+    if (mode == kFprop) {
+      int cpb = g.Cout >= 16 ? 4 : 1;
+      dim3 grid((unsigned)g.N, (unsigned)((g.Cout + cpb - 1) / cpb));
+      if (dtype == MCG_F32) fullwin_fprop_kernel<float><<<grid, 256, 0, st>>>((const float*)a, w, bias, out, ob, g.N, g.Cout, g.K, cpb);
+      else fullwin_fprop_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, w, bias, out, ob, g.N, g.Cout, g.K, cpb);
+    } else {
+      long long total = (long long)g.N * g.K;
+      long long nb = (total + 255) / 256;
+      int blocks = (int)(nb < (long long)num_sms() * 16 ? nb : (long long)num_sms() * 16);
+      if (dtype == MCG_F32) fullwin_dgrad_kernel<float><<<blocks, 256, 0, st>>>((const float*)a, w, bias, out, ob, accumulate, g.N, g.Cout, g.K, g.Cin);
+      else fullwin_dgrad_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)a, w, bias, out, ob, accumulate, g.N, g.Cout, g.K, g.Cin);
+    }
+    MCG_CHECK_LAUNCH(who);
+    return 0;
+  }
   long long Mrows, Kred;
   int Ncols;
   long long Mo = (long long)g.N * g.To * g.Ho * g.Wo, Mi = (long long)g.N * g.Ti * g.Hi * g.Wi;

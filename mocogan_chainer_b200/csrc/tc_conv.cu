@@ -528,6 +528,52 @@ __global__ void __launch_bounds__(256) im2col_kernel(const __nv_bfloat16* __rest
     *reinterpret_cast<uint4*>(cols + m * Kp + k0) = *reinterpret_cast<const uint4*>(v);
   }
 }
+// Line-staged im2col: one CTA per output line (n, to, ho).  The kT*kH source rows it needs are read coalesced into shared
+// memory (zero-padded at the borders), then the line's Wo x Kp block of cols — one contiguous span — is written with
+// 16-byte stores.  Source bytes are read ~kT*kH/(sT*sH) times from L2, cols bytes are written exactly once.
+template <int CIN, int KW>
+__global__ void __launch_bounds__(128) im2col_line_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ cols,
+                                                          int Kp, int Ti, int Hi, int Wi, int To, int Ho, int Wo, int kT, int kH,
+                                                          int sT, int sH, int sW, int pT, int pH, int pW) {
+  extern __shared__ unsigned short rows[];  // [kT*kH][L]
+  const int runs = kT * kH;
+  const int L = (Wi + pW + KW) * CIN;
+  const int K = runs * KW * CIN;
+  int line = blockIdx.x;
+  const int ho = line % Ho; line /= Ho;
+  const int to = line % To;
+  const long long n = line / To;
+  const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
+  for (int run = 0; run < runs; ++run) {
+    const int kh = run % kH, kt = run / kH;
+    const int ti = to * sT - pT + kt, hi = ho * sH - pH + kh;
+    const bool row_ok = (unsigned)ti < (unsigned)Ti && (unsigned)hi < (unsigned)Hi;
+    const long long src = (((n * Ti + ti) * Hi + hi) * (long long)Wi) * CIN;
+    for (int e = threadIdx.x; e < L; e += blockDim.x) {
+      const int w = e / CIN - pW;
+      rows[run * L + e] = (row_ok && (unsigned)w < (unsigned)Wi) ? __ldg(xs + src + (e - pW * CIN)) : (unsigned short)0;
+    }
+  }
+  __syncthreads();
+  const int vec_per_row = Kp / 8;
+  const long long m0 = ((n * To + to) * Ho + ho) * (long long)Wo;
+  uint4* dst = reinterpret_cast<uint4*>(cols + m0 * Kp);
+  for (int v = threadIdx.x; v < Wo * vec_per_row; v += blockDim.x) {
+    const int wo = v / vec_per_row, k0 = (v % vec_per_row) * 8;
+    __align__(16) unsigned short o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = k0 + i;
+      unsigned short val = 0;
+      if (k < K) {
+        const int run = k / (KW * CIN), rem = k % (KW * CIN);
+        val = rows[run * L + wo * sW * CIN + rem];
+      }
+      o[i] = val;
+    }
+    dst[v] = *reinterpret_cast<const uint4*>(o);
+  }
+}
 // wp[co][Kp] = w[co][k] (k < K) else 0
 __global__ void pad_rows_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wp, int rows, int K, int Kp) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * Kp; i += gridDim.x * blockDim.x) {
@@ -557,7 +603,7 @@ size_t tc_small_workspace(const mcg_conv_geom* g) {
 }
 
 int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b, void* out, const float* bias, int out_dtype,
-                  void* ws, size_t ws_bytes, cudaStream_t st) {
+                  void* ws, size_t ws_bytes, cudaStream_t st, bool cols_valid) {
   const char* who = mode == kFprop ? "mcg_conv_fprop(tc,small-C)" : mode == kDgrad ? "mcg_conv_dgrad(tc,small-C)" : "mcg_conv_wgrad(tc,small-C)";
   if (!tc_small_supported(g)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: needs Cin <= 16, Cout %% 64 == 0", who);
   const int taps = g->kT * g->kH * g->kW;
@@ -617,8 +663,19 @@ int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b
   }
   // fprop / wgrad: im2col, then a GEMM over a 1-D line of M pixels with Kp channels
   const void* x = a;
-  im2col_kernel<<<num_sms() * 16, 256, 0, st>>>((const __nv_bfloat16*)x, cols, M, Kp, g->Cin, g->Ti, g->Hi, g->Wi, g->To, g->Ho,
-                                                 g->Wo, g->kT, g->kH, g->kW, g->sT, g->sH, g->sW, g->pT, g->pH, g->pW);
+  if (!cols_valid) {
+    const long long lines = (long long)g->N * g->To * g->Ho;
+    const size_t smem = (size_t)g->kT * g->kH * (g->Wi + g->pW + g->kW) * g->Cin * 2;
+    if (g->kW == 4 && g->Cin == 3 && lines < 0x7fffffffLL && smem <= 48 * 1024)
+      im2col_line_kernel<3, 4><<<(unsigned)lines, 128, smem, st>>>((const __nv_bfloat16*)x, cols, Kp, g->Ti, g->Hi, g->Wi, g->To, g->Ho,
+                                                                   g->Wo, g->kT, g->kH, g->sT, g->sH, g->sW, g->pT, g->pH, g->pW);
+    else if (g->kW == 4 && g->Cin == 1 && lines < 0x7fffffffLL && smem <= 48 * 1024)
+      im2col_line_kernel<1, 4><<<(unsigned)lines, 128, smem, st>>>((const __nv_bfloat16*)x, cols, Kp, g->Ti, g->Hi, g->Wi, g->To, g->Ho,
+                                                                   g->Wo, g->kT, g->kH, g->sT, g->sH, g->sW, g->pT, g->pH, g->pW);
+    else
+      im2col_kernel<<<num_sms() * 16, 256, 0, st>>>((const __nv_bfloat16*)x, cols, M, Kp, g->Cin, g->Ti, g->Hi, g->Wi, g->To, g->Ho,
+                                                     g->Wo, g->kT, g->kH, g->kW, g->sT, g->sH, g->sW, g->pT, g->pH, g->pW);
+  }
   MCG_CHECK_LAUNCH(who);
   if (M > 0x7fffffffLL) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: too many pixels", who);
   mcg_conv_geom g2 = {1, Kp, g->Cout, 1, 1, (int)M, 1, 1, (int)M, 1, 1, 1, 1, 1, 1, 0, 0, 0};
@@ -645,17 +702,19 @@ int simt_conv(int mode, const mcg_conv_geom* c, const void* a, const void* b_act
 extern "C" {
 
 size_t mcg_conv_workspace_bytes(const mcg_conv_geom* g, int impl) {
-  if (g && impl == MCG_IMPL_TC && !tc_supported(g) && tc_small_supported(g)) return tc_small_workspace(g);
+  if (g && (impl & 0xff) == MCG_IMPL_TC && !tc_supported(g) && tc_small_supported(g)) return tc_small_workspace(g);
   return 0;
 }
 
 int mcg_conv_fprop(const mcg_conv_geom* g, const void* x, const void* w, const float* bias, void* y, int dtype,
                    int out_dtype, int impl, void* workspace, size_t workspace_bytes, void* stream) {
   if (!g || !x || !w || !y) MCG_FAIL(MCG_ERR_SHAPE, "mcg_conv_fprop: null pointer");
+  const bool cols_valid = (impl & MCG_FLAG_COLS_VALID) != 0;
+  impl &= 0xff;
   if (impl == MCG_IMPL_TC) {
     if (dtype != MCG_BF16) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_fprop(tc): activations must be bf16");
     if (!tc_supported(g) && tc_small_supported(g))
-      return tc_conv_small(0, g, x, w, y, bias, out_dtype, workspace, workspace_bytes, as_stream(stream));
+      return tc_conv_small(0, g, x, w, y, bias, out_dtype, workspace, workspace_bytes, as_stream(stream), cols_valid);
     return tc_conv(0, g, x, w, y, bias, out_dtype, as_stream(stream));
   }
   return simt_conv(0, g, x, nullptr, (const float*)w, bias, y, dtype, out_dtype, 0, as_stream(stream));
@@ -664,11 +723,12 @@ int mcg_conv_fprop(const mcg_conv_geom* g, const void* x, const void* w, const f
 int mcg_conv_dgrad(const mcg_conv_geom* g, const void* dy, const void* w, const float* bias, void* dx, int dtype,
                    int out_dtype, int accumulate, int impl, void* workspace, size_t workspace_bytes, void* stream) {
   if (!g || !dy || !w || !dx) MCG_FAIL(MCG_ERR_SHAPE, "mcg_conv_dgrad: null pointer");
+  impl &= 0xff;
   if (impl == MCG_IMPL_TC) {
     if (dtype != MCG_BF16) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_dgrad(tc): activations must be bf16");
     if (accumulate) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_dgrad(tc): accumulate not supported");
     if (!tc_supported(g) && tc_small_supported(g))
-      return tc_conv_small(1, g, dy, w, dx, bias, out_dtype, workspace, workspace_bytes, as_stream(stream));
+      return tc_conv_small(1, g, dy, w, dx, bias, out_dtype, workspace, workspace_bytes, as_stream(stream), false);
     return tc_conv(1, g, dy, w, dx, bias, out_dtype, as_stream(stream));
   }
   return simt_conv(1, g, dy, nullptr, (const float*)w, bias, dx, dtype, out_dtype, accumulate, as_stream(stream));
@@ -677,10 +737,12 @@ int mcg_conv_dgrad(const mcg_conv_geom* g, const void* dy, const void* w, const 
 int mcg_conv_wgrad(const mcg_conv_geom* g, const void* x, const void* dy, float* dw, int dtype, int impl, void* workspace,
                    size_t workspace_bytes, void* stream) {
   if (!g || !x || !dy || !dw) MCG_FAIL(MCG_ERR_SHAPE, "mcg_conv_wgrad: null pointer");
+  const bool cols_valid = (impl & MCG_FLAG_COLS_VALID) != 0;
+  impl &= 0xff;
   if (impl == MCG_IMPL_TC) {
     if (dtype != MCG_BF16) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_wgrad(tc): activations must be bf16");
     if (!tc_supported(g) && tc_small_supported(g))
-      return tc_conv_small(2, g, x, dy, dw, nullptr, MCG_F32, workspace, workspace_bytes, as_stream(stream));
+      return tc_conv_small(2, g, x, dy, dw, nullptr, MCG_F32, workspace, workspace_bytes, as_stream(stream), cols_valid);
     return tc_conv(2, g, x, dy, dw, nullptr, MCG_F32, as_stream(stream));
   }
   return simt_conv(2, g, dy, x, nullptr, nullptr, dw, dtype, MCG_F32, 1, as_stream(stream));

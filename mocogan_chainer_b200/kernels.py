@@ -76,10 +76,18 @@ def _conv_ws(g, impl, device):
     return buf, buf.numel()
 
 
-def conv_fprop(g, x, w, bias, y, impl):
-    ws, nb = _conv_ws(g, impl, x.device)
-    check(lib().mcg_conv_fprop(C.byref(g), ptr(x), ptr(w), ptr(bias), ptr(y), dt_code(x), dt_code(y), impl, ptr(ws), nb,
-                               stream()), "mcg_conv_fprop")
+COLS_VALID = 0x100
+
+
+def conv_fprop(g, x, w, bias, y, impl, ws=None, cols_valid=False):
+    """ws: optional caller-held workspace (kept alive to reuse the im2col of a small-Cin layer in wgrad)."""
+    if ws is None:
+        ws, nb = _conv_ws(g, impl, x.device)
+    else:
+        nb = ws.numel()
+    check(lib().mcg_conv_fprop(C.byref(g), ptr(x), ptr(w), ptr(bias), ptr(y), dt_code(x), dt_code(y),
+                               impl | (COLS_VALID if cols_valid else 0), ptr(ws), nb, stream()), "mcg_conv_fprop")
+    return ws
 
 
 def conv_dgrad(g, dy, w, bias, dx, impl, accumulate=False):
@@ -88,11 +96,15 @@ def conv_dgrad(g, dy, w, bias, dx, impl, accumulate=False):
                                int(accumulate), impl, ptr(ws), nb, stream()), "mcg_conv_dgrad")
 
 
-def conv_wgrad(g, x, dy, dw, impl):
+def conv_wgrad(g, x, dy, dw, impl, ws=None, cols_valid=False):
     assert dw.dtype == torch.float32
-    ws, nb = _conv_ws(g, impl, x.device)
-    check(lib().mcg_conv_wgrad(C.byref(g), ptr(x), ptr(dy), ptr(dw), dt_code(x), impl, ptr(ws), nb, stream()),
-          "mcg_conv_wgrad")
+    if ws is None:
+        ws, nb = _conv_ws(g, impl, x.device)
+    else:
+        nb = ws.numel()
+    check(lib().mcg_conv_wgrad(C.byref(g), ptr(x), ptr(dy), ptr(dw), dt_code(x), impl | (COLS_VALID if cols_valid else 0),
+                               ptr(ws), nb, stream()), "mcg_conv_wgrad")
+    return ws
 
 
 def bn_stats(y, M, Cc, gamma, beta, eps, decay, mean, invstd, scale, shift, avg_mean, avg_var):

@@ -91,10 +91,10 @@ class ImageGenerator:
                 av = self.persistent["bn%d/avg_var" % i] if update_running else None
                 bn, stats = ops.batchnorm_fwd(y, p["bn%d/gamma" % i], p["bn%d/beta" % i], am, av)
                 out = np.maximum(bn, 0)
-                acts.append((x, y, stats, out))
+                acts.append((x, y, stats, out, bn))
             else:
                 out = np.tanh(y)
-                acts.append((x, y, None, out))
+                acts.append((x, y, None, out, None))
             x = out
         cache["acts"] = acts
         cache["z"] = z
@@ -106,7 +106,7 @@ class ImageGenerator:
         grads = {}
         g = gx.reshape(T * N, self.out_channels, 64, 64).astype(self.dtype)
         for i in range(5, 0, -1):
-            x, y, stats, out = cache["acts"][i - 1]
+            x, y, stats, out, _ = cache["acts"][i - 1]
             if i == 5:
                 g = g * (1 - out * out)
             else:
@@ -364,3 +364,18 @@ def build_models(config, dtype=np.float32, seed=0, n_filters=64):
     Di = ImageDiscriminator(C, out, n_filters, True, 0.2, rng=rng, dtype=dtype)
     Dv = VideoDiscriminator(C, out, n_filters, True, 0.2, rng=rng, dtype=dtype)
     return model, G, Di, Dv
+
+
+def kink_margin(trace):
+    """Smallest |pre-activation| / rms over every ReLU / LeakyReLU input of the step (generator and the four
+    discriminator calls).  The gradient is discontinuous at 0, so when this margin is within float32 round-off
+    (~1e-6) a float32 implementation may legitimately land on the other side of the kink than the float64 truth;
+    parity tests relax their gradient bound for that case instead of failing on a measure-zero event."""
+    m = np.inf
+    for key in ("cache_ri", "cache_rv", "cache_fi", "cache_fv"):
+        for (_, _, _, pre) in trace[key]["acts"][:4]:
+            m = min(m, float(np.abs(pre).min() / np.sqrt(np.mean(pre * pre))))
+    for a in trace["cache_g"]["acts"][:4]:
+        bn = a[4]
+        m = min(m, float(np.abs(bn).min() / np.sqrt(np.mean(bn * bn))))
+    return m
