@@ -1,0 +1,151 @@
+"""Host-side logic that needs no GPU: the autograd sweep, dead-branch pruning, link/parameter naming (the npz key
+schema of SURVEY.md App. D), iterators, flags."""
+import numpy as np
+import torch
+
+from mocogan_chainer_b200 import chainer
+from mocogan_chainer_b200.chainer import FunctionNode, Variable
+
+
+class Mul(FunctionNode):
+    calls = []
+
+    def __init__(self, tag):
+        super(Mul, self).__init__()
+        self.tag = tag
+
+    def forward(self, inputs):
+        return inputs[0] * inputs[1],
+
+    def backward(self, idx, gys):
+        Mul.calls.append((self.tag, idx))
+        a, b = self.inputs
+        out = {0: gys[0] * b.data, 1: gys[0] * a.data}
+        return tuple(out[i] for i in idx)
+
+
+def test_backward_accumulates_and_orders_by_rank():
+    Mul.calls = []
+    x = Variable(torch.tensor([2.0]))
+    w = Variable(torch.tensor([3.0]))
+    h = Mul("h").apply((x, w))[0]          # 6
+    y = Mul("y").apply((h, h))[0]          # 36 = (xw)^2
+    y.backward()
+    assert float(x.grad) == 2 * 6 * 3 and float(w.grad) == 2 * 6 * 2
+    assert [c[0] for c in Mul.calls] == ["y", "h"]
+
+
+def test_dead_branches_are_never_launched():
+    """SURVEY §3.2 pts 2,4: a stopped variable prunes every backward kernel that only feeds it."""
+    Mul.calls = []
+    x = Variable(torch.tensor([2.0]))
+    frozen = Variable(torch.tensor([5.0]))
+    w = Variable(torch.tensor([3.0]))
+    h = Mul("h").apply((x, frozen))[0]
+    y = Mul("y").apply((h, w))[0]
+    x.stop = frozen.stop = True
+    y.backward()
+    assert Mul.calls == [("y", (1,))]       # no dgrad towards h, node "h" never runs
+    assert x.grad is None and float(w.grad) == 10.0
+    x.stop = False
+    Mul.calls = []
+    w.cleargrad()
+    y.backward()
+    assert Mul.calls == [("y", (0, 1)), ("h", (0,))]
+
+
+def test_requires_grad_false_inputs_get_no_gradient():
+    Mul.calls = []
+    x = Variable(torch.tensor([2.0]), requires_grad=False)
+    w = Variable(torch.tensor([3.0]))
+    y = Mul("y").apply((x, w))[0]
+    y.backward()
+    assert Mul.calls == [("y", (1,))]
+
+
+def test_param_names_match_chainer_npz_schema():
+    from mocogan_chainer_b200.model.net import ImageDiscriminator, ImageGenerator, VideoDiscriminator
+    np.random.seed(0)
+    G = ImageGenerator(50, 10, 6, 3, 8, 16)
+    names = [n.lstrip("/") for n, _ in G.namedparams()]
+    for k in ("g0/W_r/W", "g0/U_z/b", "g0/W/W", "g0/U/b", "dc1/W", "dc5/b", "bn1/gamma", "bn4/beta"):
+        assert k in names
+    shapes = {n.lstrip("/"): p.shape for n, p in G.namedparams()}
+    assert shapes["g0/W_r/W"] == (10, 16) and shapes["g0/U_r/W"] == (10, 10)
+    assert shapes["dc1/W"] == (60, 64, 4, 4) and shapes["dc5/W"] == (8, 3, 4, 4)      # deconv: (in, out, kh, kw)
+    Dv = VideoDiscriminator(3, 7, 8, True, 0.2)
+    shapes = {n.lstrip("/"): p.shape for n, p in Dv.namedparams()}
+    assert shapes["dc1/W"] == (8, 3, 4, 4, 4) and shapes["dc5/W"] == (7, 64, 4, 4, 4)
+    pers = [p.lstrip("/") for p, _, _ in Dv.namedpersistents()]
+    assert "bn2/avg_mean" in pers and "bn4/avg_var" in pers and "bn3/N" in pers
+    assert ImageDiscriminator().count_params() == 2766529 and ImageGenerator(50, 10, 6).count_params() == 3250827
+    assert VideoDiscriminator().count_params() == 11057857
+    assert G.name == "ImageGenerator" and Dv.name == "VideoDiscriminator" and G.dc1.name == "dc1"
+
+
+def test_internal_weight_layout_is_channels_last_of_chainer_layout():
+    from mocogan_chainer_b200.chainer import Parameter
+    a = np.arange(2 * 3 * 4 * 5, dtype=np.float32).reshape(2, 3, 4, 5)
+    p = Parameter(a, channels_last_weight=True)
+    assert p.internal_shape == (2, 4, 5, 3)
+    assert np.array_equal(p._internal_init(), np.moveaxis(a, 1, -1))
+    t = torch.from_numpy(p._internal_init().copy())
+    assert np.array_equal(p._to_logical(t).numpy(), a)
+
+
+def test_serial_iterator_epochs_and_concat():
+    from mocogan_chainer_b200.chainer.dataset import concat_examples
+    from mocogan_chainer_b200.chainer.iterators import SerialIterator
+    data = [(np.full((1, 2), i, np.float32), i % 3) for i in range(10)]
+    it = SerialIterator(data, 4, shuffle=False)
+    b1 = it.next()
+    assert [int(t) for _, t in b1] == [0, 1, 2] + [0] and not it.is_new_epoch
+    it.next()
+    b3 = it.next()
+    assert it.is_new_epoch and it.epoch == 1 and len(b3) == 4
+    x, t = concat_examples(b1)
+    assert x.shape == (4, 1, 2) and list(t) == [0, 1, 2, 0]
+    x, t = concat_examples([(np.zeros(3, np.float32), None)] * 2)   # Moving-MNIST labels are None (datasets.py:166)
+    assert t is None and x.shape == (2, 3)
+
+
+def test_glorot_and_lecun_statistics():
+    from mocogan_chainer_b200.chainer import initializers as I
+    np.random.seed(1)
+    w = I.GlorotNormal()((256, 128, 4, 4))
+    assert abs(w.std() - np.sqrt(2.0 / ((128 + 256) * 16))) < 2e-4
+    w = I.LeCunNormal()((10, 16))
+    assert w.shape == (10, 16) and w.dtype == np.float32
+
+
+def test_adam_lr_schedule_matches_chainer_formula():
+    import math
+    opt = chainer.optimizers.Adam(alpha=2e-4, beta1=5e-5)
+    opt.t = 3
+    assert abs(opt.lr - 2e-4 * math.sqrt(1 - 0.999 ** 3) / (1 - (5e-5) ** 3)) < 1e-18
+
+
+def test_train_flags_match_reference_defaults():
+    from mocogan_chainer_b200.train import build_parser
+    a = build_parser().parse_args([])
+    assert (a.gpu, a.dataset_type, a.dataset, a.batchsize, a.max_epoch, a.model) == (-1, 'mug', 'data/dataset/train', 100,
+                                                                                    1000, 'normal')
+    assert (a.display_interval, a.snapshot_interval, a.log_tensorboard_interval, a.num_gen_samples) == (1, 10, 10, 36)
+    assert (a.dim_zc, a.dim_zm, a.n_filters_gen, a.n_filters_idis, a.n_filters_vdis, a.resume) == (50, 10, 64, 64, 64, '')
+    a = build_parser().parse_args(['-g', '0', '-r', 'x.npz', '--model', 'infogan', '--dataset_type', 'mnist'])
+    assert a.gpu == 0 and a.resume == 'x.npz' and a.model == 'infogan'
+    from mocogan_chainer_b200.generate_samples import build_parser as gp
+    g = gp().parse_args(['w.npz', 'out'])
+    assert (g.model_weight, g.save_path, g.num, g.gpu) == ('w.npz', 'out', 36, -1)
+
+
+def test_model_wiring_follows_train_py():
+    import pytest
+    from mocogan_chainer_b200.train import build_models
+    np.random.seed(0)
+    g, di, dv = build_models("infogan", 50, 10, 6, 3, 8, 16, True, 0.2)
+    assert di.out_channels == 7 and dv.out_channels == 7 and g.dim_zl == 6 and di.use_noise and dv.noise_sigma == 0.2
+    g, di, dv = build_models("cgan", 50, 10, 6, 3, 8, 16, True, 0.2)
+    assert di.in_channels == 9 and dv.in_channels == 9
+    with pytest.raises(ValueError):
+        build_models("cgan", 50, 10, 0, 3, 8, 16, True, 0.2)

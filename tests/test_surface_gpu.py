@@ -1,0 +1,59 @@
+"""train.py / generate_samples.py drop-in surface on the GPU: a short synthetic training run (eager and CUDA-graph),
+npz snapshots with the reference's key schema, and generate_samples loading them."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _needs_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+
+
+def test_train_then_generate(tmp_path, monkeypatch):
+    from mocogan_chainer_b200 import generate_samples, train
+    monkeypatch.chdir(tmp_path)
+    up = train.main(["-g", "0", "--synthetic", "12", "--batchsize", "4", "--max_epoch", "2", "--snapshot_interval", "1",
+                     "--n_filters_gen", "64", "--save_name", "run", "--model", "infogan", "--graph"])
+    assert up.iteration == 6 and up.epoch == 2 and up._graph is not None
+    for v in up.losses.values():
+        assert np.isfinite(float(v))
+    out = tmp_path / "result" / "run"
+    for f in ("image_gen_epoch_1.npz", "video_dis_epoch_2.npz", "image_dis_epoch_fianl.npz"):
+        assert (out / f).exists()
+    with np.load(out / "image_gen_epoch_fianl.npz") as f:
+        assert f["dc1/W"].shape == (60, 512, 4, 4) and f["g0/W_r/W"].shape == (10, 16)
+        assert f["bn1/avg_mean"].shape == (512,) and "bn4/N" in f.files
+        assert np.abs(f["bn1/avg_mean"]).max() > 0      # running statistics were updated by training
+    videos = generate_samples.main([str(out / "image_gen_epoch_fianl.npz"), str(tmp_path / "gen"), "-n", "4"])
+    assert videos.shape == (16, 4, 3, 64, 64) and videos.dtype == np.uint8
+    assert os.path.exists(tmp_path / "gen" / "videos.npy")
+
+
+def test_graph_replay_equals_eager_with_same_seed():
+    """The captured step must be the same computation as the eager step: identical weights after 4 steps."""
+    from mocogan_chainer_b200 import chainer
+    from mocogan_chainer_b200 import random as mrandom
+    from tests.test_step_gpu import build_pair
+    res = []
+    for graph in (False, True):
+        np.random.seed(0)
+        chainer.config.compute_dtype = "fp32"
+        _, (G, Di, Dv), _, up, _ = build_pair("mug_normal", 8, "fp32")
+        up.use_graph, up.graph_warmup = graph, 1
+        mrandom.set_source(mrandom.DeviceRandom(seed=7, video_length=16))
+        x = torch.from_numpy(np.random.default_rng(0).uniform(-1, 1, (2, 3, 16, 64, 64)).astype(np.float32)).cuda()
+        t = torch.tensor([1, 4], dtype=torch.int32, device="cuda")
+        for _ in range(4):
+            up.step_host_inputs(x, t)
+        torch.cuda.synchronize()
+        assert (up._graph is not None) == graph
+        res.append(torch.cat([m.arena().data.clone() for m in (G, Di, Dv)]))
+    # wgrad uses fp32 atomics (order-dependent rounding), so compare to fp32 round-off amplified by 4 Adam steps
+    assert (res[0] - res[1]).abs().max().item() < 5e-4
+    assert (res[0] - res[1]).abs().mean().item() < 1e-5
