@@ -114,8 +114,9 @@ static int launch_colreduce(F f, const void* p0, const void* p1, long long M, in
   if (CG > kRedThreads) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: C=%d has too many channel groups", name, C);
   const int tpr = pow2_ge(CG);
   const int rpb = kRedThreads / tpr;
-  long long want = (M + rpb - 1) / rpb;
+  long long want = (M + (long long)rpb * 8 - 1) / ((long long)rpb * 8);  // >= 8 rows per thread: few partials to finalize
   int nblk = (int)(want < kRedMaxBlocks ? want : kRedMaxBlocks);
+  if (nblk < 1) nblk = 1;
   if (ws_bytes < (size_t)nblk * 2 * C * sizeof(float) || !ws)
     MCG_FAIL(MCG_ERR_WORKSPACE, "%s: workspace %zu < %zu", name, ws_bytes, (size_t)nblk * 2 * C * sizeof(float));
   size_t smem = (size_t)kRedThreads * 2 * VEC * sizeof(float);
@@ -133,12 +134,20 @@ static int launch_colreduce(F f, const void* p0, const void* p1, long long M, in
 // One warp per channel: lanes stride over the per-block partials, then a shuffle tree (fixed order: deterministic).
 __device__ __forceinline__ void warp_sum_partials(const float* partial, int nblk, int C, int c, double& s, double& q) {
   const int lane = threadIdx.x & 31;
-  s = 0;
-  q = 0;
-  for (int b = lane; b < nblk; b += 32) {
-    s += partial[(size_t)b * 2 * C + c];
-    q += partial[(size_t)b * 2 * C + C + c];
+  double s0 = 0, s1 = 0, q0 = 0, q1 = 0;
+  int b = lane;
+  for (; b + 32 < nblk; b += 64) {  // two independent chains so the loads of consecutive iterations overlap
+    s0 += partial[(size_t)b * 2 * C + c];
+    q0 += partial[(size_t)b * 2 * C + C + c];
+    s1 += partial[(size_t)(b + 32) * 2 * C + c];
+    q1 += partial[(size_t)(b + 32) * 2 * C + C + c];
   }
+  if (b < nblk) {
+    s0 += partial[(size_t)b * 2 * C + c];
+    q0 += partial[(size_t)b * 2 * C + C + c];
+  }
+  s = s0 + s1;
+  q = q0 + q1;
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
     q += __shfl_xor_sync(0xffffffffu, q, o);
@@ -235,27 +244,33 @@ __global__ void __launch_bounds__(256) pack_video_kernel(
     long long s_h, long long s_w, const int* __restrict__ frame_ptr, float sigma, const float* __restrict__ noise,
     long long ns_n, long long ns_c, long long ns_p, const StepState* __restrict__ rng, int call_id,
     TO* __restrict__ out) {
+  // one thread per pixel: for a channels-first source the reads of each channel are coalesced along w and the C
+  // outputs of a pixel are adjacent, so a warp writes one contiguous span
   const int Tout = frame_ptr ? 1 : T;
   const int t0 = frame_ptr ? *frame_ptr : 0;
-  const long long total = (long long)N * Tout * H * W * C;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(idx % C);
-    long long r = idx / C;
-    int w = (int)(r % W); r /= W;
-    int h = (int)(r % H); r /= H;
-    int t = (int)(r % Tout);
-    long long n = r / Tout;
-    float v = ld<TI>(src, n * s_n + (long long)c * s_c + (long long)(t + t0) * s_t + (long long)h * s_h + (long long)w * s_w);
-    if (noise) {
-      long long p = ((long long)t * H + h) * W + w;  // position inside the (T',H,W) block the noise tensor covers
-      v += sigma * noise[n * ns_n + (long long)c * ns_c + p * ns_p];
-    } else if (rng && sigma != 0.f) {
-      float z[4];
-      philox_normal4(rng, call_id, (unsigned long long)idx, z);
-      v += sigma * z[0];
+  const long long pixels = (long long)N * Tout * H * W;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < pixels;
+       pix += (long long)gridDim.x * blockDim.x) {
+    long long r = pix;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H); r /= H;
+    const int t = (int)(r % Tout);
+    const long long n = r / Tout;
+    const long long sbase = n * s_n + (long long)(t + t0) * s_t + (long long)h * s_h + (long long)w * s_w;
+    const long long p = ((long long)t * H + h) * W + w;  // position inside the (T',H,W) block the noise tensor covers
+    for (int c0 = 0; c0 < C; c0 += 4) {
+      float z[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!noise && rng && sigma != 0.f) philox_normal4(rng, call_id, (unsigned long long)pix * ((C + 3) / 4) + c0 / 4, z);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + i;
+        if (c >= C) break;
+        float v = ld<TI>(src, sbase + (long long)c * s_c);
+        if (noise) v += sigma * noise[n * ns_n + (long long)c * ns_c + p * ns_p];
+        else v += sigma * z[i];
+        st<TO>(out, pix * C + c, v);
+      }
     }
-    st<TO>(out, idx, v);
   }
 }
 
@@ -492,7 +507,7 @@ int mcg_pack_video(const void* src, int src_dtype, int N, int C, int T, int H, i
     MCG_FAIL(MCG_ERR_SHAPE, "mcg_pack_video: bad arguments");
   if (!dtype_ok(src_dtype) || !dtype_ok(out_dtype)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_pack_video: dtype");
   cudaStream_t st = as_stream(stream);
-  long long total = (long long)N * (frame_ptr ? 1 : T) * H * W * C;
+  long long total = (long long)N * (frame_ptr ? 1 : T) * H * W;
   dispatch2(src_dtype, out_dtype, [&](auto ti, auto to) {
     using TI = decltype(ti);
     using TO = decltype(to);

@@ -188,19 +188,31 @@ template <typename T>
 __global__ void __launch_bounds__(256) fullwin_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w,
                                                             const float* __restrict__ bias, void* __restrict__ dx,
                                                             int out_bf16, int accumulate, int M, int Cout, int K, int Cin) {
-  const long long total = (long long)M * K;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int m = (int)(idx / K), k = (int)(idx % K);
-    float acc = bias ? bias[k % Cin] : 0.f;
-    for (int co = 0; co < Cout; ++co) acc = fmaf(ld<T>(dy, (long long)m * Cout + co), w[(long long)co * K + k], acc);
+  // four consecutive k per thread (K % 4 == 0 is checked by the launcher; Cin % 4 == 0 keeps a quad inside one pixel)
+  const long long quads = (long long)M * (K / 4);
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(q / (K / 4)), k = (int)(q % (K / 4)) * 4;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (bias) { a0 = bias[k % Cin]; a1 = bias[(k + 1) % Cin]; a2 = bias[(k + 2) % Cin]; a3 = bias[(k + 3) % Cin]; }
+    const T* dr = dy + (long long)m * Cout;
+    for (int co = 0; co < Cout; ++co) {
+      const float d = ld<T>(dr, co);
+      const float4 wv = *reinterpret_cast<const float4*>(w + (long long)co * K + k);
+      a0 = fmaf(d, wv.x, a0); a1 = fmaf(d, wv.y, a1); a2 = fmaf(d, wv.z, a2); a3 = fmaf(d, wv.w, a3);
+    }
+    const long long o = (long long)m * K + k;
     if (out_bf16) {
-      __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(dx);
-      if (accumulate) acc += __bfloat162float(p[idx]);
-      p[idx] = __float2bfloat16_rn(acc);
+      __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(dx) + o;
+      if (accumulate) { a0 += __bfloat162float(p[0]); a1 += __bfloat162float(p[1]); a2 += __bfloat162float(p[2]); a3 += __bfloat162float(p[3]); }
+      __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(p) = u;
     } else {
-      float* p = reinterpret_cast<float*>(dx);
-      if (accumulate) acc += p[idx];
-      p[idx] = acc;
+      float* p = reinterpret_cast<float*>(dx) + o;
+      if (accumulate) { a0 += p[0]; a1 += p[1]; a2 += p[2]; a3 += p[3]; }
+      *reinterpret_cast<float4*>(p) = make_float4(a0, a1, a2, a3);
     }
   }
 }
@@ -236,7 +248,7 @@ int simt_conv(int mode, const mcg_conv_geom* c, const void* a, const void* b_act
   if (int rc = make_geo(c, &g, who)) return rc;
   if (dtype != MCG_F32 && dtype != MCG_BF16) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: dtype %d", who, dtype);
   static const bool no_fullwin = getenv("MCG_NO_FULLWIN") != nullptr;  // debugging aid
-  if (!no_fullwin && is_full_window(g) && mode != kWgrad) {
+  if (!no_fullwin && is_full_window(g) && mode != kWgrad && (mode == kFprop || g.K % 4 == 0)) {
     const int ob = out_dtype == MCG_BF16;
     if (mode == kFprop) {
       int cpb = g.Cout >= 16 ? 4 : 1;
@@ -244,7 +256,7 @@ int simt_conv(int mode, const mcg_conv_geom* c, const void* a, const void* b_act
       if (dtype == MCG_F32) fullwin_fprop_kernel<float><<<grid, 256, 0, st>>>((const float*)a, w, bias, out, ob, g.N, g.Cout, g.K, cpb);
       else fullwin_fprop_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, w, bias, out, ob, g.N, g.Cout, g.K, cpb);
     } else {
-      long long total = (long long)g.N * g.K;
+      long long total = (long long)g.N * (g.K / 4);
       long long nb = (total + 255) / 256;
       int blocks = (int)(nb < (long long)num_sms() * 16 ? nb : (long long)num_sms() * 16);
       if (dtype == MCG_F32) fullwin_dgrad_kernel<float><<<blocks, 256, 0, st>>>((const float*)a, w, bias, out, ob, accumulate, g.N, g.Cout, g.K, g.Cin);

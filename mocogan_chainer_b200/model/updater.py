@@ -27,6 +27,9 @@ class Updater(chainer.training.StandardUpdater):
         # additive (not in the reference): CUDA-graph capture of the device part of the step
         self.use_graph = kwargs.pop('use_graph', False)
         self.graph_warmup = kwargs.pop('graph_warmup', 2)
+        # additive: run the (small) image discriminator on a second stream, concurrently with the video discriminator
+        self.use_streams = kwargs.pop('use_streams', True)
+        self._side = None
 
         super(Updater, self).__init__(*args, **kwargs)
         self.losses = {}
@@ -83,7 +86,15 @@ class Updater(chainer.training.StandardUpdater):
         if self.model == 'cgan':
             x_real = self.concat_label_video(x_real, t_real)
         t = src.frame()                                   # updater.py:96, stays on the device
-        y_real_i = image_dis(x_real, frame=t)             # updater.py:97
+        main = torch.cuda.current_stream()
+        side = main
+        if self.use_streams:
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            side = self._side
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            y_real_i = image_dis(x_real, frame=t)         # updater.py:97   (side stream: ~30 small launches)
         y_real_v = video_dis(x_real)                      # updater.py:98
 
         ## fake data
@@ -92,16 +103,22 @@ class Updater(chainer.training.StandardUpdater):
         t_fake = None if t_fake is None else Variable(t_fake, requires_grad=False)
         if self.model == 'cgan':
             raise NotImplementedError("cgan needs the label planes on the attached fake clip (SURVEY.md §8f rank 4)")
-        y_fake_i = image_dis(x_fake, frame=t)             # updater.py:107
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            y_fake_i = image_dis(x_fake, frame=t)         # updater.py:107
         y_fake_v = video_dis(x_fake)                      # updater.py:108
 
         ## update  (updater.py:111-113)
         # passes A, B: gradients flowing from the discriminator losses into the generator are discarded by the
         # reference (image_gen.cleargrads() in pass C) -> not computed.  pass C: discriminator wgrads are discarded.
+        # Passes A and B touch disjoint parameters and activations, so A runs on the side stream while B runs on the
+        # main stream; both are complete before pass C reads the updated discriminator weights.
         image_dis_optimizer.stop_variables = video_dis_optimizer.stop_variables = (x_fake,)
         image_gen_optimizer.frozen_links = (image_dis, video_dis)
-        image_dis_optimizer.update(self.loss_dis, image_dis, y_real_i, y_fake_i, t_real, t_fake)
+        with torch.cuda.stream(side):
+            image_dis_optimizer.update(self.loss_dis, image_dis, y_real_i, y_fake_i, t_real, t_fake)
         video_dis_optimizer.update(self.loss_dis, video_dis, y_real_v, y_fake_v, t_real, t_fake)
+        main.wait_stream(side)
         image_gen_optimizer.update(self.loss_gen, image_gen, y_fake_i, y_fake_v, t_fake)
 
     # ------------------------------------------------------------------ update_core
