@@ -274,6 +274,25 @@ __global__ void __launch_bounds__(256) pack_video_kernel(
   }
 }
 
+// Same operation, one thread per ELEMENT: used when the source is channel-contiguous with many channels (dtype / layout
+// conversions of activations), where consecutive threads then read consecutive addresses.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) pack_elem_kernel(const TI* __restrict__ src, int N, int C, int T, int H, int W,
+                                                        long long s_n, long long s_c, long long s_t, long long s_h,
+                                                        long long s_w, TO* __restrict__ out) {
+  const long long total = (long long)N * T * H * W * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    long long r = idx / C;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H); r /= H;
+    const int t = (int)(r % T);
+    const long long n = r / T;
+    st<TO>(out, idx, ld<TI>(src, n * s_n + (long long)c * s_c + (long long)t * s_t + (long long)h * s_h + (long long)w * s_w));
+  }
+}
+
 // =====================================================================================================
 // backward of (BN ->) activation, apply half
 // =====================================================================================================
@@ -508,6 +527,17 @@ int mcg_pack_video(const void* src, int src_dtype, int N, int C, int T, int H, i
   if (!dtype_ok(src_dtype) || !dtype_ok(out_dtype)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_pack_video: dtype");
   cudaStream_t st = as_stream(stream);
   long long total = (long long)N * (frame_ptr ? 1 : T) * H * W;
+  const bool plain = !frame_ptr && !noise && (sigma == 0.f || !rng_state);
+  if (plain && C > 4) {   // pure layout / dtype conversion of a wide tensor
+    dispatch2(src_dtype, out_dtype, [&](auto ti, auto to) {
+      using TI = decltype(ti);
+      using TO = decltype(to);
+      pack_elem_kernel<TI, TO><<<grid_for(total * C), 256, 0, st>>>((const TI*)src, N, C, T, H, W, s_n, s_c, s_t, s_h, s_w,
+                                                                     (TO*)out);
+    });
+    MCG_CHECK_LAUNCH("mcg_pack_video(elem)");
+    return 0;
+  }
   dispatch2(src_dtype, out_dtype, [&](auto ti, auto to) {
     using TI = decltype(ti);
     using TO = decltype(to);

@@ -19,7 +19,7 @@
 
 namespace mcg {
 
-enum { kFprop = 0, kDgrad = 1, kWgrad = 2, kDgradSmall = 3 };  // kDgradSmall: dgrad with <= 16 input channels
+enum { kFprop = 0, kDgrad = 1, kWgrad = 2 };
 
 struct TcTap {
   int16_t dw, dh, dt, kidx;  // A-box coordinate offsets; kidx = linear tap index (kt,kh,kw)
@@ -39,6 +39,8 @@ struct TcParams {
   int total_boxes, boxes_per_split;                           // wgrad
   int total_slabs, kreal;                                     // wgrad: valid 64-row slabs; real row length of dw
   int out_f32;
+  int planar_chunk, planar_cols;   // fprop: write column c to plane c/chunk as [plane][pixel][chunk] (0 = row-major)
+  long long planar_stride;
   TcTap taps[64];
 };
 
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
   }
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));  // power of two >= BN
   if (warp == 1) { tmem_alloc(&tmem_slot, TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -115,8 +117,6 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
                       h0 * P.a_mul_h + P.a_add_h + tp.dh, t0 * P.a_mul_t + P.a_add_t + tp.dt, n0);
           if (MODE == kFprop) {
             tma_load_2d(b_dst, &mapB, &full_bar[s], tp.kidx * P.Cin + c * 64, ncol0);
-          } else if (MODE == kDgradSmall) {  // transposed weights (16 padded ci rows) x (taps*Cout), K-major
-            tma_load_2d(b_dst, &mapB, &full_bar[s], tp.kidx * P.Cout + c * 64, 0);
           } else {
 #pragma unroll
             for (int sl = 0; sl < BN / 64; ++sl)
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
   } else if (warp == 1) {
     // ================================================= MMA issuer ===========================================
     if (lane == 0) {
-      constexpr int A_MN = (MODE == kWgrad), B_MN = (MODE == kDgrad || MODE == kWgrad);
+      constexpr int A_MN = (MODE == kWgrad), B_MN = (MODE != kFprop);
       const uint32_t idesc = make_idesc_bf16(128, BN, A_MN, B_MN);
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % STAGES;
@@ -182,18 +182,6 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
         const int on = n0 + ib;
         const bool valid = ow < P.full_w && oh < P.full_h && ot < P.full_t && on < P.EN;
         const long long base = (long long)on * P.os_n + (long long)ot * P.os_t + (long long)oh * P.os_h + (long long)ow * P.os_w + ncol0;
-        if (MODE == kDgradSmall) {
-          uint32_t v[16];
-          tmem_ld16(tmem + (uint32_t(q * 32) << 16), v);
-          tmem_ld_wait();
-          if (valid) {
-            for (int i = 0; i < P.Cin; ++i) {
-              const float f = __uint_as_float(v[i]) + (bias ? bias[i] : 0.f);
-              if (P.out_f32) reinterpret_cast<float*>(out)[base + i] = f;
-              else reinterpret_cast<__nv_bfloat16*>(out)[base + i] = __float2bfloat16_rn(f);
-            }
-          }
-        } else
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
@@ -203,7 +191,22 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
             float f[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + (bias ? bias[ncol0 + c0 + i] : 0.f);
-            if (P.out_f32) {
+            if (MODE == kFprop && P.planar_chunk) {
+              // planar bf16 output for the narrow-Cin dgrad GEMM: plane = (kt,kh) run, so col2im reads contiguous lines
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const int c = ncol0 + c0 + i;
+                if (c < P.planar_cols) {
+                  const int plane = c / P.planar_chunk, within = c - plane * P.planar_chunk;
+                  uint2 u;
+                  __nv_bfloat162 lo = __floats2bfloat162_rn(f[i], f[i + 1]), hi = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
+                  u.x = *reinterpret_cast<uint32_t*>(&lo);
+                  u.y = *reinterpret_cast<uint32_t*>(&hi);
+                  *reinterpret_cast<uint2*>(o + plane * P.planar_stride + (long long)ow * P.planar_chunk + within) = u;
+                }
+              }
+            } else if (P.out_f32) {
               float* o = reinterpret_cast<float*>(out) + base + c0;
 #pragma unroll
               for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
@@ -336,6 +339,7 @@ static int pick_bn(int cols, long long mtiles) {
   // widest tile that still gives every SM work; columns must divide
   int best = 64;
   const int sms = num_sms();
+  if (cols == 192) return 192;  // the 3-channel layers' (tap, ci) axis: one N tile, A read once
   for (int bn = 256; bn >= 64; bn /= 2) {
     if (cols % bn) continue;
     long long ctas = mtiles * (cols / bn);
@@ -348,7 +352,7 @@ template <int MODE, int BN>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, dim3 grid, void* out, const float* bias,
                      cudaStream_t st, const char* who) {
   constexpr int STAGE = A_BYTES + BN * 128;
-  constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : (BN == 64 ? 4 : 6));  // BN<=128: ~96 KB so two CTAs share an SM
+  constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 3 : 4));  // BN<=128: ~96 KB so two CTAs share an SM
   size_t smem = (size_t)STAGES * STAGE + 1024;
   static bool configured = false;
   if (!configured) {
@@ -366,6 +370,7 @@ static int launch_tc_bn(int bn, const CUtensorMap& ma, const CUtensorMap& mb, co
   switch (bn) {
     case 64: return launch_tc<MODE, 64>(ma, mb, P, grid, out, bias, st, who);
     case 128: return launch_tc<MODE, 128>(ma, mb, P, grid, out, bias, st, who);
+    case 192: return launch_tc<MODE, 192>(ma, mb, P, grid, out, bias, st, who);
     case 256: return launch_tc<MODE, 256>(ma, mb, P, grid, out, bias, st, who);
   }
   MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: BN=%d", who, bn);
@@ -380,7 +385,7 @@ bool tc_supported(const mcg_conv_geom* g) {
 }
 
 int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void* out, const float* bias, int out_dtype,
-            cudaStream_t st, int kreal = 0) {
+            cudaStream_t st, int kreal = 0, int planar_chunk = 0, int planar_cols = 0) {
   const char* who = mode == kFprop ? "mcg_conv_fprop(tc)" : mode == kDgrad ? "mcg_conv_dgrad(tc)" : "mcg_conv_wgrad(tc)";
   if (!tc_supported(g)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: needs Cin,Cout %% 64 == 0, stride <= 2, <= 64 taps", who);
   TcParams P;
@@ -388,6 +393,9 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
   const int taps = g->kT * g->kH * g->kW;
   P.Cin = g->Cin; P.Cout = g->Cout; P.Ktot = taps * g->Cin;
   P.out_f32 = (out_dtype == MCG_F32);
+  P.planar_chunk = planar_chunk;
+  P.planar_cols = planar_cols;
+  P.planar_stride = (long long)g->Wo * planar_chunk;   // planar mode is only used on 1-D line geometries (M = Wo)
   CUtensorMap ma, mb;
   int rc;
   if (mode == kFprop) {
@@ -476,7 +484,10 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
       if (g->Cout % c == 0) { bn = c; break; }
     P.total_boxes = P.nbw * P.nbh * P.nbt * P.nbb;
     long long tiles = (long long)mtiles * (g->Cout / bn);
-    long long want = (2LL * num_sms() + tiles - 1) / tiles;
+    // one full wave: resident CTAs per SM is 2 for BN <= 128 (96 KB of stages), 1 for BN = 256; rounding the split
+    // count UP spills a few CTAs into a second wave that doubles the kernel time (ncu: Dv.dc2, 320 CTAs on 296 slots)
+    const long long slots = (long long)num_sms() * (bn <= 128 ? 2 : 1);
+    long long want = slots / tiles;
     long long maxs = ceil_div(P.total_boxes, 8);
     int splits = (int)(want < maxs ? want : maxs);
     if (splits < 1) splits = 1;
@@ -495,7 +506,7 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
 //   fprop / wgrad : x is expanded once into an explicit im2col matrix cols[M][Kp] (Kp = taps*Cin rounded up to 64) in
 //                   caller workspace and the layer becomes a plain GEMM = a 1x1 "convolution" over a 1-D line of M
 //                   pixels through the same tcgen05 kernel;
-//   dgrad         : output has Cin <= 16 channels -> kDgradSmall (N = 16 MMA, transposed zero-padded weights).
+//   dgrad         : Z[M][Kp] = dy . w^T as the same kind of GEMM (N = taps*Cin), then a line-staged col2im gather.
 // These layers are HBM/L2-bound (Dv.dc1 writes 29.8 M outputs, G.dc5 reads 36.7 M inputs), not tensor-bound.
 // =============================================================================================================
 __global__ void __launch_bounds__(256) im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ cols,
@@ -581,25 +592,84 @@ __global__ void pad_rows_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat
     wp[i] = k < K ? w[(long long)r * K + k] : __float2bfloat16_rn(0.f);
   }
 }
-// wt[ci (16 rows, zero-padded)][tap*Cout + co] = w[co][tap][ci]
-__global__ void transpose_small_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wt, int Cout, int taps,
-                                       int Cin) {
-  const int cols = taps * Cout;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 16 * cols; i += gridDim.x * blockDim.x) {
-    const int ci = i / cols, rem = i % cols, tap = rem / Cout, co = rem % Cout;
-    wt[i] = ci < Cin ? w[((long long)co * taps + tap) * Cin + ci] : __float2bfloat16_rn(0.f);
+// wt[j = (tap, ci), zero-padded to Jp rows][co] = w[co][tap][ci]   (K-major B operand of the dgrad GEMM)
+__global__ void transpose_jk_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wt, int Cout, int J,
+                                    int Jp) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Jp * Cout; i += gridDim.x * blockDim.x) {
+    const int j = i / Cout, co = i % Cout;
+    wt[i] = j < J ? w[(long long)co * J + j] : __float2bfloat16_rn(0.f);
+  }
+}
+// col2im for the narrow-Cin dgrad: dx[n,ti,hi,wi,ci] = bias[ci] + sum over taps of Z[pixel(to,ho,wo)][tap*Cin+ci].
+// One CTA per input line (n, ti, hi): the (kt,kh) runs that reach this line are gathered from Z into shared memory
+// (each a run of kW*Cin contiguous elements per output pixel), then the line's Wi*Cin outputs are summed in fp32.
+__global__ void __launch_bounds__(128) col2im_line_kernel(const __nv_bfloat16* __restrict__ Z, const float* __restrict__ bias,
+                                                          void* __restrict__ dx, int out_f32, long long Mpix, int Cin, int Ti, int Hi,
+                                                          int Wi, int To, int Ho, int Wo, int kT, int kH, int kW, int sT, int sH,
+                                                          int sW, int pT, int pH, int pW) {
+  extern __shared__ unsigned short zs[];  // [valid runs][Wo][kW*Cin]
+  __shared__ int run_row[64], run_col[64];
+  __shared__ int nvalid;
+  const int RUN = kW * Cin;
+  int line = blockIdx.x;
+  const int hi = line % Hi; line /= Hi;
+  const int ti = line % Ti;
+  const long long n = line / Ti;
+  if (threadIdx.x == 0) {
+    int v = 0;
+    for (int kt = 0; kt < kT; ++kt) {
+      const int tt = ti + pT - kt;
+      if (tt < 0 || tt % sT || tt / sT >= To) continue;
+      for (int kh = 0; kh < kH; ++kh) {
+        const int hh = hi + pH - kh;
+        if (hh < 0 || hh % sH || hh / sH >= Ho) continue;
+        run_row[v] = (int)(((n * To + tt / sT) * Ho + hh / sH));   // Z row block (times Wo)
+        run_col[v] = kt * kH + kh;                                  // plane index
+        ++v;
+      }
+    }
+    nvalid = v;
+  }
+  __syncthreads();
+  const int nv = nvalid;
+  // Z is planar: Z[run][pixel][RUN]; a line needs, per valid run, Wo*RUN contiguous elements
+  const uint32_t* zsrc = reinterpret_cast<const uint32_t*>(Z);
+  uint32_t* zs32 = reinterpret_cast<uint32_t*>(zs);
+  const int words = Wo * RUN / 2;
+  for (int v = 0; v < nv; ++v) {
+    const long long base = ((long long)run_col[v] * Mpix + (long long)run_row[v] * Wo) * RUN / 2;
+    for (int e = threadIdx.x; e < words; e += blockDim.x) zs32[v * words + e] = __ldg(zsrc + base + e);
+  }
+  __syncthreads();
+  const long long obase = ((n * Ti + ti) * Hi + hi) * (long long)Wi * Cin;
+  for (int o = threadIdx.x; o < Wi * Cin; o += blockDim.x) {
+    const int wi = o / Cin, ci = o % Cin;
+    float acc = bias ? bias[ci] : 0.f;
+    for (int kw = 0; kw < kW; ++kw) {
+      const int ww = wi + pW - kw;
+      if (ww < 0 || ww % sW) continue;
+      const int wo = ww / sW;
+      if (wo >= Wo) continue;
+      for (int v = 0; v < nv; ++v) {
+        const __nv_bfloat16_raw raw = {zs[(v * Wo + wo) * RUN + kw * Cin + ci]};
+        acc += __bfloat162float(__nv_bfloat16(raw));
+      }
+    }
+    if (out_f32) reinterpret_cast<float*>(dx)[obase + o] = acc;
+    else reinterpret_cast<__nv_bfloat16*>(dx)[obase + o] = __float2bfloat16_rn(acc);
   }
 }
 
 static long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 
 bool tc_small_supported(const mcg_conv_geom* g) {
-  return g->Cin <= 16 && g->Cout % 64 == 0 && g->sT <= 2 && g->sH <= 2 && g->sW <= 2 && g->kT * g->kH * g->kW <= 64;
+  return g->Cin <= 16 && g->Cout % 64 == 0 && g->sT <= 2 && g->sH <= 2 && g->sW <= 2 && g->kT * g->kH * g->kW <= 64 &&
+         g->kW % 4 == 0;
 }
 size_t tc_small_workspace(const mcg_conv_geom* g) {
   const long long M = (long long)g->N * g->To * g->Ho * g->Wo;
   const long long K = (long long)g->kT * g->kH * g->kW * g->Cin, Kp = round_up(K, 64);
-  return (size_t)(M * Kp * 2 + round_up((long long)g->Cout * Kp * 2, 1024) + round_up(16LL * g->kT * g->kH * g->kW * g->Cout * 2, 1024) + 4096);
+  return (size_t)(round_up(M * Kp * 2, 1024) + round_up((long long)g->Cout * Kp * 2, 1024) + 4096);
 }
 
 int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b, void* out, const float* bias, int out_dtype,
@@ -615,51 +685,23 @@ int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b
   __nv_bfloat16* wpad = reinterpret_cast<__nv_bfloat16*>(base + round_up(M * Kp * 2, 1024));
   int rc;
   if (mode == kDgrad) {
-    // a = dy (N,To,Ho,Wo,Cout), b = w bf16 (Cout,taps,Cin), out = dx (N,Ti,Hi,Wi,Cin)
-    __nv_bfloat16* wt = wpad;
-    transpose_small_kernel<<<64, 256, 0, st>>>((const __nv_bfloat16*)b, wt, g->Cout, taps, g->Cin);
+    // a = dy (N,To,Ho,Wo,Cout), b = w bf16 (Cout,taps,Cin), out = dx (N,Ti,Hi,Wi,Cin):
+    //   Z[M][Kp] = dy[M][Cout] . wt[Kp][Cout]^T  (tcgen05 GEMM over the line of M output pixels), then col2im.
+    if (M > 0x7fffffffLL) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: too many pixels", who);
+    transpose_jk_kernel<<<64, 256, 0, st>>>((const __nv_bfloat16*)b, wpad, g->Cout, K, Kp);
     MCG_CHECK_LAUNCH(who);
-    TcParams P;
-    memset(&P, 0, sizeof(P));
-    P.Cin = g->Cin; P.Cout = g->Cout; P.Ktot = K;
-    P.out_f32 = (out_dtype == MCG_F32);
-    const int cw = g->sW, ch = g->sH, ct = g->sT;
-    const int EW = ceil_div(g->Wi, cw), EH = ceil_div(g->Hi, ch), ET = ceil_div(g->Ti, ct);
-    Box bx = choose_box(128, EW, EH, ET, g->N);
-    P.BW = bx.w; P.BH = bx.h; P.BT = bx.t; P.BB = bx.b;
-    P.nbw = ceil_div(EW, bx.w); P.nbh = ceil_div(EH, bx.h); P.nbt = ceil_div(ET, bx.t); P.nbb = ceil_div(g->N, bx.b);
-    P.EW = EW; P.EH = EH; P.ET = ET; P.EN = g->N;
-    P.full_w = g->Wi; P.full_h = g->Hi; P.full_t = g->Ti;
-    P.a_mul_w = P.a_mul_h = P.a_mul_t = 1;
-    P.o_mul_w = cw; P.o_mul_h = ch; P.o_mul_t = ct;
-    P.cls_w = cw; P.cls_h = ch; P.cls_t = ct;
-    P.os_w = g->Cin; P.os_h = (long long)g->Wi * g->Cin; P.os_t = (long long)g->Hi * P.os_h; P.os_n = (long long)g->Ti * P.os_t;
-    P.chunks = g->Cout / 64;
-    int ncls = cw * ch * ct, j = 0;
-    for (int c = 0; c < ncls; ++c) {
-      const int pw = c % cw, ph = (c / cw) % ch, pt = c / (cw * ch);
-      P.tap_begin[c] = j;
-      for (int kt = 0; kt < g->kT; ++kt) {
-        if ((pt + g->pT - kt) % ct) continue;
-        for (int kh = 0; kh < g->kH; ++kh) {
-          if ((ph + g->pH - kh) % ch) continue;
-          for (int kw = 0; kw < g->kW; ++kw) {
-            if ((pw + g->pW - kw) % cw) continue;
-            P.taps[j++] = TcTap{(int16_t)((pw + g->pW - kw) / cw), (int16_t)((ph + g->pH - kh) / ch),
-                                (int16_t)((pt + g->pT - kt) / ct), (int16_t)((kt * g->kH + kh) * g->kW + kw)};
-          }
-        }
-      }
-      P.tap_count[c] = j - P.tap_begin[c];
-    }
-    CUtensorMap ma, mb;
-    if ((rc = act_map(&ma, a, g->Cout, g->Wo, g->Ho, g->To, g->N, bx.w, bx.h, bx.t, bx.b, 1, 1, 1))) return rc;
-    uint64_t d2[2] = {(uint64_t)taps * g->Cout, 16}, s2[1] = {(uint64_t)taps * g->Cout * 2};
-    uint32_t b2[2] = {64, 16}, e2[2] = {1, 1};
-    if ((rc = get_map(&mb, wt, 2, d2, s2, b2, e2))) return rc;
-    long long mt = (long long)P.nbw * P.nbh * P.nbt * P.nbb * ncls;
-    dim3 grid((unsigned)mt, 1, 1);
-    return launch_tc<kDgradSmall, 16>(ma, mb, P, grid, out, bias, st, who);
+    mcg_conv_geom g2 = {1, g->Cout, Kp, 1, 1, (int)M, 1, 1, (int)M, 1, 1, 1, 1, 1, 1, 0, 0, 0};
+    const int RUN = g->kW * g->Cin;
+    if ((rc = tc_conv(kFprop, &g2, a, wpad, cols, nullptr, MCG_BF16, st, 0, RUN, K))) return rc;
+    const long long lines = (long long)g->N * g->Ti * g->Hi;
+    const int runs_max = ceil_div(g->kT, g->sT) * ceil_div(g->kH, g->sH);
+    const size_t smem = (size_t)runs_max * g->Wo * g->kW * g->Cin * 2;
+    if (lines > 0x7fffffffLL || smem > 48 * 1024 || g->kT * g->kH > 64) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: line too large", who);
+    col2im_line_kernel<<<(unsigned)lines, 128, smem, st>>>(cols, bias, out, out_dtype == MCG_F32, M, g->Cin, g->Ti, g->Hi, g->Wi,
+                                                           g->To, g->Ho, g->Wo, g->kT, g->kH, g->kW, g->sT, g->sH, g->sW, g->pT,
+                                                           g->pH, g->pW);
+    MCG_CHECK_LAUNCH(who);
+    return 0;
   }
   // fprop / wgrad: im2col, then a GEMM over a 1-D line of M pixels with Kp channels
   const void* x = a;

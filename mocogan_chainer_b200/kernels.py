@@ -65,7 +65,7 @@ def tc_ok(g):
         return False
     if max(g.sT, g.sH, g.sW) > 2 or g.kT * g.kH * g.kW > 64 or g.Cout % 64:
         return False
-    return g.Cin % 64 == 0 or g.Cin <= 16
+    return g.Cin % 64 == 0 or (g.Cin <= 16 and g.kW % 4 == 0)
 
 
 def _conv_ws(g, impl, device):

@@ -30,6 +30,9 @@ class Updater(chainer.training.StandardUpdater):
         # additive: run the (small) image discriminator on a second stream, concurrently with the video discriminator
         self.use_streams = kwargs.pop('use_streams', True)
         self._side = None
+        # additive: in graph mode, copy batch i+1 host->device on a copy stream while step i runs
+        self.prefetch = kwargs.pop('prefetch', True)
+        self._stage, self._stage_next, self._copy_stream, self._flags = None, None, None, None
 
         super(Updater, self).__init__(*args, **kwargs)
         self.losses = {}
@@ -122,17 +125,72 @@ class Updater(chainer.training.StandardUpdater):
         image_gen_optimizer.update(self.loss_gen, image_gen, y_fake_i, y_fake_v, t_fake)
 
     # ------------------------------------------------------------------ update_core
-    def update_core(self):
-        ## real data  (updater.py:87-92)
-        batch = self.get_iterator('main').next()
+    def _next_host_batch(self):
+        it = self.get_iterator('main')
+        batch = it.next()
         x_real, t_real = concat_examples(batch)
         if t_real is not None and not torch.is_tensor(t_real):
             t_real = np.asarray(t_real).astype(np.int32)
+        return x_real, t_real, (it.is_new_epoch, it.epoch)
+
+    @property
+    def is_new_epoch(self):
+        return self._flags[0] if self._flags is not None else self._iterators['main'].is_new_epoch
+
+    @property
+    def epoch(self):
+        return self._flags[1] if self._flags is not None else self._iterators['main'].epoch
+
+    def update_core(self):
+        ## real data  (updater.py:87-92)
+        if self.use_graph and self.prefetch:
+            return self._update_core_prefetched()
+        x_real, t_real, _ = self._next_host_batch()
         if self.use_graph:
             return self.step_host_inputs(x_real, t_real)
         x_real = self.converter(x_real, self.device)
         t_real = None if t_real is None else self.converter(t_real, self.device)
         self.step_on_device(x_real, t_real)
+
+    def _issue_h2d(self, k, host):
+        """Starts the host->device copy of one batch into staging slot k on the copy stream."""
+        as_t = lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+        x, t, flags = host
+        x = as_t(x)
+        t = None if t is None else as_t(t)
+        slot = self._stage[k]
+        if slot is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            slot = self._stage[k] = {"x": torch.empty(x.shape, dtype=x.dtype, device=dev),
+                                     "t": None if t is None else torch.empty(t.shape, dtype=torch.int32, device=dev),
+                                     "ready": torch.cuda.Event(), "consumed": None}
+        cs = self._copy_stream
+        if slot["consumed"] is not None:
+            cs.wait_event(slot["consumed"])        # the step that read this slot has copied it out
+        with torch.cuda.stream(cs):
+            slot["x"].copy_(x, non_blocking=True)
+            if t is not None:
+                slot["t"].copy_(t, non_blocking=True)
+            slot["ready"].record(cs)
+        slot["flags"] = flags
+
+    def _update_core_prefetched(self):
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._stage = [None, None]
+            self._stage_next = 0
+            self._issue_h2d(0, self._next_host_batch())
+        k = self._stage_next
+        slot = self._stage[k]
+        main = torch.cuda.current_stream()
+        main.wait_event(slot["ready"])
+        self._flags = slot["flags"]
+        self._stage_next = 1 - k
+        self._issue_h2d(1 - k, self._next_host_batch())      # overlaps with the step launched below
+        self.step_host_inputs(slot["x"], slot["t"])           # device->static copy + graph replay on `main`
+        ev = torch.cuda.Event()
+        ev.record(main)
+        slot["consumed"] = ev
 
     def step_host_inputs(self, x_real, t_real):
         """CUDA-graph path: the batch (host or device) is copied straight into static device buffers, the device part
