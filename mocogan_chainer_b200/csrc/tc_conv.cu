@@ -16,6 +16,7 @@
 #include <mutex>
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 
 namespace mcg {
 
@@ -36,9 +37,17 @@ struct TcParams {
   int chunks;                                                 // 64-channel K chunks per tap (fprop/dgrad)
   int Cin, Cout, Ktot;                                        // Ktot = taps*Cin (row length of w / dw)
   int tap_begin[8], tap_count[8];
-  int total_boxes, boxes_per_split;                           // wgrad
+  // Schedule: every CTA owns one contiguous range of `units` (persistent, one CTA per SM).
+  // fprop/dgrad: unit = one 128-pixel box of one row = (cls, nt); a CTA walks its range MT boxes at a time (the last
+  // step of a row or range may hold fewer), so the work per CTA differs by at most one box.
+  // wgrad: unit = one K step (pixel box) of one tile = (mgroup of MT blocks of 2 slabs of 64 (tap,ci) rows, nt); a tile
+  // cut between CTAs (stream-K) meets again in the fp32 red.add of the epilogue.
+  int nboxes, ntn, ntiles;
+  long long total_units, units_per_cta;
+  int total_boxes;                                            // wgrad: K steps per tile
   int total_slabs, kreal;                                     // wgrad: valid 64-row slabs; real row length of dw
-  int out_f32;
+  int debug_skip_epi;
+  int out_f32, ocols;                                        // ocols = channels of one output pixel row
   int planar_chunk, planar_cols;   // fprop: write column c to plane c/chunk as [plane][pixel][chunk] (0 = row-major)
   long long planar_stride;
   TcTap taps[64];
@@ -49,199 +58,353 @@ __device__ int g_tc_error = 0;
 constexpr int kTcThreads = 192;
 constexpr int A_BYTES = 128 * 128;  // 128 rows x 64 bf16
 
-template <int MODE, int BN, int STAGES>
-__global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                             const __grid_constant__ CUtensorMap mapB,
-                                                             const __grid_constant__ TcParams P, void* __restrict__ out,
-                                                             const float* __restrict__ bias) {
+struct TcSeg {
+  int tile, k0, nk;    // K steps [k0, k0 + nk) of `tile` (fprop/dgrad: tile = row (cls, nt), all of its K steps)
+  int box0, nlive;     // fprop/dgrad: first pixel box and number of 128-row blocks (<= MT) of this step
+};
+// The same deterministic segment sequence is walked by the producer, the MMA issuer and the epilogue warps.
+template <int MODE, int MT>
+struct TcSegIter {
+  long long u, u_end;
+  __device__ __forceinline__ explicit TcSegIter(const TcParams& P) {
+    u = (long long)blockIdx.x * P.units_per_cta;
+    u_end = u + P.units_per_cta;
+    if (u_end > P.total_units) u_end = P.total_units;
+  }
+  __device__ __forceinline__ bool next(const TcParams& P, TcSeg& s) {
+    if (u >= u_end) return false;
+    if (MODE == kWgrad) {
+      s.tile = (int)(u / P.total_boxes);
+      s.k0 = (int)(u - (long long)s.tile * P.total_boxes);
+      long long n = P.total_boxes - s.k0;
+      if (n > u_end - u) n = u_end - u;
+      s.nk = (int)n;
+      s.box0 = 0; s.nlive = MT;
+      u += n;
+      return true;
+    }
+    s.tile = (int)(u / P.nboxes);
+    s.box0 = (int)(u - (long long)s.tile * P.nboxes);
+    long long n = P.nboxes - s.box0;
+    if (n > u_end - u) n = u_end - u;
+    if (n > MT) n = MT;
+    s.nlive = (int)n;
+    s.k0 = 0;
+    s.nk = P.tap_count[s.tile / P.ntn] * P.chunks;
+    u += n;
+    return true;
+  }
+};
+
+struct TcBox { int w0, h0, t0, n0; };
+__device__ __forceinline__ TcBox tc_decode_box(const TcParams& P, int bi) {
+  TcBox b;
+  b.w0 = (bi % P.nbw) * P.BW; bi /= P.nbw;
+  b.h0 = (bi % P.nbh) * P.BH; bi /= P.nbh;
+  b.t0 = (bi % P.nbt) * P.BT; bi /= P.nbt;
+  b.n0 = bi * P.BB;
+  return b;
+}
+
+// column sums over the warp's 32 rows of a 32-column chunk: after the butterfly lane j holds the sum of column j
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+template <int MODE, int BN, int MT, int STAGES, int OCC>
+__global__ void __launch_bounds__(kTcThreads, OCC) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                const __grid_constant__ CUtensorMap mapB,
+                                                                const __grid_constant__ TcParams P, void* __restrict__ out,
+                                                                const float* __restrict__ bias, float* __restrict__ stats) {
   constexpr int B_BYTES = BN * 128;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
+  constexpr int ACC_COLS = MT * BN;                       // fp32 accumulator columns of one tile
+  constexpr int NBUF = (2 * ACC_COLS <= 512 / OCC) ? 2 : 1;   // double-buffered accumulators when they fit in TMEM (512 columns per SM, shared by OCC CTAs)
+  constexpr int TMEM_NEED = NBUF * ACC_COLS;
+  constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : (TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512)));
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], done_bar;
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* err = &g_tc_error;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(&done_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
     fence_barrier_init();
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
   }
-  constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));  // power of two >= BN
   if (warp == 1) { tmem_alloc(&tmem_slot, TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  // ---- tile decode ---------------------------------------------------------------------------------------
-  int cls = 0, w0 = 0, h0 = 0, t0 = 0, n0 = 0;
-  int nk = 0;
-  int pb_begin = 0;
-  if (MODE != kWgrad) {
-    int b = blockIdx.x;
-    int bw = b % P.nbw; b /= P.nbw;
-    int bh = b % P.nbh; b /= P.nbh;
-    int bt = b % P.nbt; b /= P.nbt;
-    int bb = b % P.nbb; b /= P.nbb;
-    cls = b;
-    w0 = bw * P.BW; h0 = bh * P.BH; t0 = bt * P.BT; n0 = bb * P.BB;
-    nk = P.tap_count[cls] * P.chunks;
-  } else {
-    pb_begin = blockIdx.z * P.boxes_per_split;
-    int pe = pb_begin + P.boxes_per_split;
-    if (pe > P.total_boxes) pe = P.total_boxes;
-    nk = pe - pb_begin;
-    if (nk < 0) nk = 0;
-  }
-  const int ncol0 = blockIdx.y * BN;
+  const uint32_t smem_a = smem_u32(smem);
+  const uint32_t full_a = smem_u32(&full_bar[0]), empty_a = smem_u32(&empty_bar[0]);
+  const uint32_t tfull_a = smem_u32(&tfull_bar[0]), tempty_a = smem_u32(&tempty_bar[0]);
 
   if (warp == 0) {
     // ================================================= TMA producer =========================================
-    if (lane == 0) {
-      int u0 = blockIdx.x * 2;  // wgrad: the two 64-row slabs = (tap, chunk) pairs u0, u0+1
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        if (!mbar_wait(&empty_bar[s], ph ^ 1, err)) break;
-        uint8_t* a_dst = smem + s * STAGE_BYTES;
-        uint8_t* b_dst = a_dst + A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+    // ONE elected thread; the loop is instruction-bound, so everything per K step is strength-reduced: no divisions,
+    // tap / slab decode hoisted, barrier and stage addresses advanced incrementally.
+    if (elect_one()) {
+      const uint64_t map_a = reinterpret_cast<uint64_t>(&mapA), map_b = reinterpret_cast<uint64_t>(&mapB);
+      TcSegIter<MODE, MT> iter(P);
+      TcSeg sg;
+      int s = 0;
+      uint32_t ph = 1;   // ring slot and the parity its `empty` barrier is waited with
+      uint32_t stage_a = smem_a, full_s = full_a, empty_s = empty_a;
+      bool alive = true;
+      while (alive && iter.next(P, sg)) {
+        const int nt = sg.tile % P.ntn, mg = sg.tile / P.ntn;
+        const int ncol0 = nt * BN;
         if (MODE != kWgrad) {
-          const int j = P.tap_begin[cls] + kb / P.chunks, c = kb % P.chunks;
-          const TcTap tp = P.taps[j];
-          tma_load_5d(a_dst, &mapA, &full_bar[s], c * 64, w0 * P.a_mul_w + P.a_add_w + tp.dw,
-                      h0 * P.a_mul_h + P.a_add_h + tp.dh, t0 * P.a_mul_t + P.a_add_t + tp.dt, n0);
-          if (MODE == kFprop) {
-            tma_load_2d(b_dst, &mapB, &full_bar[s], tp.kidx * P.Cin + c * 64, ncol0);
-          } else {
+          const int cls = mg;
+          TcBox bx[MT];
 #pragma unroll
-            for (int sl = 0; sl < BN / 64; ++sl)
-              tma_load_2d(b_dst + sl * 8192, &mapB, &full_bar[s], tp.kidx * P.Cin + ncol0 + sl * 64, c * 64);
+          for (int m = 0; m < MT; ++m) {
+            bx[m] = tc_decode_box(P, sg.box0 + (m < sg.nlive ? m : 0));
+            bx[m].w0 = bx[m].w0 * P.a_mul_w + P.a_add_w;
+            bx[m].h0 = bx[m].h0 * P.a_mul_h + P.a_add_h;
+            bx[m].t0 = bx[m].t0 * P.a_mul_t + P.a_add_t;
+          }
+          const uint32_t tx_bytes = sg.nlive * A_BYTES + B_BYTES;
+          const int j_end = P.tap_begin[cls] + P.tap_count[cls], chunks = P.chunks;
+          for (int j = P.tap_begin[cls]; alive && j < j_end; ++j) {
+            const TcTap tp = P.taps[j];
+            const int kcol = tp.kidx * P.Cin;
+            for (int c = 0; c < chunks; ++c) {
+              if (!mbar_wait_a(empty_s, ph, err)) { alive = false; break; }
+              mbar_expect_tx_a(full_s, tx_bytes);
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                if (m < sg.nlive)
+                  tma_load_5d_a(stage_a + m * A_BYTES, map_a, full_s, c * 64, bx[m].w0 + tp.dw, bx[m].h0 + tp.dh,
+                                bx[m].t0 + tp.dt, bx[m].n0);
+              if (MODE == kFprop) {
+                tma_load_2d_a(stage_a + MT * A_BYTES, map_b, full_s, kcol + c * 64, ncol0);
+              } else {
+#pragma unroll
+                for (int sl = 0; sl < BN / 64; ++sl)
+                  tma_load_2d_a(stage_a + MT * A_BYTES + sl * 8192, map_b, full_s, kcol + ncol0 + sl * 64, c * 64);
+              }
+              ++s; stage_a += STAGE_BYTES; full_s += 8; empty_s += 8;
+              if (s == STAGES) { s = 0; ph ^= 1; stage_a = smem_a; full_s = full_a; empty_s = empty_a; }
+            }
           }
         } else {
-          int pb = pb_begin + kb;
-          int bw = pb % P.nbw; pb /= P.nbw;
-          int bh = pb % P.nbh; pb /= P.nbh;
-          int bt = pb % P.nbt; pb /= P.nbt;
-          int bb = pb;
-          const int pw0 = bw * P.BW, ph0 = bh * P.BH, pt0 = bt * P.BT, pn0 = bb * P.BB;
+          const int u0 = mg * MT * 2;  // first of the tile's MT*2 slabs = (tap, chunk) pairs
+          int sc[MT * 2], sw[MT * 2], sh[MT * 2], st_[MT * 2];
 #pragma unroll
-          for (int sl = 0; sl < 2; ++sl) {
+          for (int sl = 0; sl < MT * 2; ++sl) {
             const int u = u0 + sl;
-            const bool live = u < P.total_slabs;  // an odd slab count leaves one dummy slab: channel coordinate out of
-            const TcTap tp = P.taps[live ? u / P.chunks : 0];  // bounds -> TMA zero-fills it
-            tma_load_5d(a_dst + sl * 8192, &mapA, &full_bar[s], live ? (u % P.chunks) * 64 : P.Cin, pw0 * P.a_mul_w + P.a_add_w + tp.dw,
-                        ph0 * P.a_mul_h + P.a_add_h + tp.dh, pt0 * P.a_mul_t + P.a_add_t + tp.dt, pn0);
+            const bool live = u < P.total_slabs;  // a dummy slab's channel coordinate is out of bounds -> zero fill
+            const TcTap tp = P.taps[live ? u / P.chunks : 0];
+            sc[sl] = live ? (u % P.chunks) * 64 : P.Cin;
+            sw[sl] = P.a_add_w + tp.dw; sh[sl] = P.a_add_h + tp.dh; st_[sl] = P.a_add_t + tp.dt;
           }
+          TcBox pb = tc_decode_box(P, sg.k0);
+          const int wlim = P.nbw * P.BW, hlim = P.nbh * P.BH, tlim = P.nbt * P.BT;
+          const int BWs = P.BW, BHs = P.BH, BTs = P.BT, BBs = P.BB, mw = P.a_mul_w, mh = P.a_mul_h, mt_ = P.a_mul_t;
+          for (int kb = 0; kb < sg.nk; ++kb) {
+            if (!mbar_wait_a(empty_s, ph, err)) { alive = false; break; }
+            mbar_expect_tx_a(full_s, STAGE_BYTES);
+            const int aw = pb.w0 * mw, ah = pb.h0 * mh, at = pb.t0 * mt_;
 #pragma unroll
-          for (int sl = 0; sl < BN / 64; ++sl)
-            tma_load_5d(b_dst + sl * 8192, &mapB, &full_bar[s], ncol0 + sl * 64, pw0, ph0, pt0, pn0);
+            for (int sl = 0; sl < MT * 2; ++sl)
+              tma_load_5d_a(stage_a + sl * 8192, map_a, full_s, sc[sl], aw + sw[sl], ah + sh[sl], at + st_[sl], pb.n0);
+#pragma unroll
+            for (int sl = 0; sl < BN / 64; ++sl)
+              tma_load_5d_a(stage_a + MT * A_BYTES + sl * 8192, map_b, full_s, ncol0 + sl * 64, pb.w0, pb.h0, pb.t0, pb.n0);
+            ++s; stage_a += STAGE_BYTES; full_s += 8; empty_s += 8;
+            if (s == STAGES) { s = 0; ph ^= 1; stage_a = smem_a; full_s = full_a; empty_s = empty_a; }
+            pb.w0 += BWs;   // next pixel box, carried by hand
+            if (pb.w0 >= wlim) {
+              pb.w0 = 0; pb.h0 += BHs;
+              if (pb.h0 >= hlim) {
+                pb.h0 = 0; pb.t0 += BTs;
+                if (pb.t0 >= tlim) { pb.t0 = 0; pb.n0 += BBs; }
+              }
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ================================================= MMA issuer ===========================================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr int A_MN = (MODE == kWgrad), B_MN = (MODE != kFprop);
+      constexpr uint32_t A_KSTEP = (A_MN ? 2048 : 32) >> 4, B_KSTEP = (B_MN ? 2048 : 32) >> 4;   // per K=16 slice, in 16-B units
       const uint32_t idesc = make_idesc_bf16(128, BN, A_MN, B_MN);
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        if (!mbar_wait(&full_bar[s], ph, err)) break;
+      const uint32_t desc_hi = smem_desc_hi(1024);
+      const uint32_t a_lo0 = smem_desc_lo(smem_a, A_MN ? 8192 : 16), b_lo0 = smem_desc_lo(smem_a + MT * A_BYTES, B_MN ? 8192 : 16);
+      TcSegIter<MODE, MT> iter(P);
+      TcSeg sg;
+      uint32_t seg = 0, ph = 0;
+      int s = 0;
+      uint32_t a_lo = a_lo0, b_lo = b_lo0, full_s = full_a, empty_s = empty_a;
+      bool alive = true;
+      while (alive && iter.next(P, sg)) {
+        if (sg.nk == 0) continue;
+        const uint32_t buf = seg % NBUF;
+        if (!mbar_wait_a(tempty_a + buf * 8, ((seg / NBUF) & 1) ^ 1, err)) break;
         tc_fence_after();
-        const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), b0 = a0 + A_BYTES;
+        const uint32_t acc = tmem + buf * ACC_COLS;
+        const int nlive = sg.nlive;
+        for (int kb = 0; kb < sg.nk; ++kb) {
+          if (!mbar_wait_a(full_s, ph, err)) { alive = false; break; }
+          tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = A_MN ? make_smem_desc(a0 + k * 2048, 8192, 1024) : make_smem_desc(a0 + k * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_smem_desc(b0 + k * 2048, 8192, 1024) : make_smem_desc(b0 + k * 32, 16, 1024);
-          umma_bf16(tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
+          for (int m = 0; m < MT; ++m) {
+            if (m >= nlive) break;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_lh(acc + m * BN, a_lo + m * (A_BYTES >> 4) + k * A_KSTEP, desc_hi, b_lo + k * B_KSTEP, desc_hi, idesc,
+                           (kb | k) ? 1u : 0u);
+          }
+          umma_commit_a(empty_s);
+          ++s; a_lo += STAGE_BYTES >> 4; b_lo += STAGE_BYTES >> 4; full_s += 8; empty_s += 8;
+          if (s == STAGES) { s = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; full_s = full_a; empty_s = empty_a; }
         }
-        umma_commit(&empty_bar[s]);
+        if (alive) umma_commit_a(tfull_a + buf * 8);
+        ++seg;
       }
-      umma_commit(&done_bar);
     }
   } else {
     // ================================================= epilogue ============================================
     const int q = warp & 3;
     const int r = q * 32 + lane;  // accumulator row == TMEM lane
-    const bool ok = (nk > 0) && mbar_wait(&done_bar, 0, err);
-    tc_fence_after();
-    if (ok) {
+    TcSegIter<MODE, MT> iter(P);
+    TcSeg sg;
+    uint32_t seg = 0;
+    while (iter.next(P, sg)) {
+      const int nt = sg.tile % P.ntn, mg = sg.tile / P.ntn;
+      const int ncol0 = nt * BN;
+      const bool have_acc = sg.nk > 0;
+      const uint32_t buf = seg % NBUF;
+      if (have_acc) {
+        if (!mbar_wait_a(tfull_a + buf * 8, (seg / NBUF) & 1, err)) break;
+        tc_fence_after();
+      }
+      const uint32_t acc = tmem + (uint32_t(q * 32) << 16) + buf * ACC_COLS;
       if (MODE != kWgrad) {
+        const int cls = mg;
+        const int pw = cls % P.cls_w, phh = (cls / P.cls_w) % P.cls_h, pt = cls / (P.cls_w * P.cls_h);
         int rr = r;
         const int iw = rr % P.BW; rr /= P.BW;
         const int ih = rr % P.BH; rr /= P.BH;
-        const int it = rr % P.BT; rr /= P.BT;
+        const int itt = rr % P.BT; rr /= P.BT;
         const int ib = rr;
-        const int pw = cls % P.cls_w, phh = (cls / P.cls_w) % P.cls_h, pt = cls / (P.cls_w * P.cls_h);
-        const int ow = (w0 + iw) * P.o_mul_w + pw, oh = (h0 + ih) * P.o_mul_h + phh, ot = (t0 + it) * P.o_mul_t + pt;
-        const int on = n0 + ib;
-        const bool valid = ow < P.full_w && oh < P.full_h && ot < P.full_t && on < P.EN;
-        const long long base = (long long)on * P.os_n + (long long)ot * P.os_t + (long long)oh * P.os_h + (long long)ow * P.os_w + ncol0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem + (uint32_t(q * 32) << 16) + c0, v);
-          tmem_ld_wait();
-          if (valid) {
+        for (int m = 0; m < sg.nlive; ++m) {
+          const TcBox bx = tc_decode_box(P, sg.box0 + m);
+          const int ow = (bx.w0 + iw) * P.o_mul_w + pw, oh = (bx.h0 + ih) * P.o_mul_h + phh, ot = (bx.t0 + itt) * P.o_mul_t + pt;
+          const int on = bx.n0 + ib;
+          const bool valid = ow < P.full_w && oh < P.full_h && ot < P.full_t && on < P.EN;
+          const long long base = (long long)on * P.os_n + (long long)ot * P.os_t + (long long)oh * P.os_h + (long long)ow * P.os_w + ncol0;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            if (have_acc) {
+              tmem_ld32(acc + m * BN + c0, v);
+              tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0u;
+            }
             float f[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + (bias ? bias[ncol0 + c0 + i] : 0.f);
-            if (MODE == kFprop && P.planar_chunk) {
-              // planar bf16 output for the narrow-Cin dgrad GEMM: plane = (kt,kh) run, so col2im reads contiguous lines
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+            if (valid) {
+              if (MODE == kFprop && P.planar_chunk) {
+                // planar bf16 output for the narrow-Cin dgrad GEMM: plane = (kt,kh) run, so col2im reads contiguous lines
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const int c = ncol0 + c0 + i;
-                if (c < P.planar_cols) {
-                  const int plane = c / P.planar_chunk, within = c - plane * P.planar_chunk;
-                  uint2 u;
-                  __nv_bfloat162 lo = __floats2bfloat162_rn(f[i], f[i + 1]), hi = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
-                  u.x = *reinterpret_cast<uint32_t*>(&lo);
-                  u.y = *reinterpret_cast<uint32_t*>(&hi);
-                  *reinterpret_cast<uint2*>(o + plane * P.planar_stride + (long long)ow * P.planar_chunk + within) = u;
+                for (int i = 0; i < 32; i += 4) {
+                  const int c = ncol0 + c0 + i;
+                  if (c < P.planar_cols) {
+                    const int plane = c / P.planar_chunk, within = c - plane * P.planar_chunk;
+                    uint2 u;
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(f[i], f[i + 1]), hi = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
+                    u.x = *reinterpret_cast<uint32_t*>(&lo);
+                    u.y = *reinterpret_cast<uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(o + plane * P.planar_stride + (long long)ow * P.planar_chunk + within) = u;
+                  }
+                }
+              } else if (P.out_f32) {
+                float* o = reinterpret_cast<float*>(out) + base + c0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+              } else {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + base + c0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                  uint4 u;
+                  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+                  h[0] = __floats2bfloat162_rn(f[i], f[i + 1]);
+                  h[1] = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
+                  h[2] = __floats2bfloat162_rn(f[i + 4], f[i + 5]);
+                  h[3] = __floats2bfloat162_rn(f[i + 6], f[i + 7]);
+                  *reinterpret_cast<uint4*>(o + i) = u;
                 }
               }
-            } else if (P.out_f32) {
-              float* o = reinterpret_cast<float*>(out) + base + c0;
+            }
+            if (stats) {
+              // BatchNorm statistics of the values just produced (what the next pass would re-read from HBM): per-column
+              // sum and sum of squares over this warp's 32 rows, one fp32 red.add per column per warp.
+              float sq[32];
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-            } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + base + c0;
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 u;
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-                h[0] = __floats2bfloat162_rn(f[i], f[i + 1]);
-                h[1] = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
-                h[2] = __floats2bfloat162_rn(f[i + 4], f[i + 5]);
-                h[3] = __floats2bfloat162_rn(f[i + 6], f[i + 7]);
-                *reinterpret_cast<uint4*>(o + i) = u;
+              for (int i = 0; i < 32; ++i) {
+                if (!valid) f[i] = 0.f;
+                else if (!P.out_f32) f[i] = __bfloat162float(__float2bfloat16_rn(f[i]));   // statistics of the stored values
+                sq[i] = f[i] * f[i];
               }
+              const float s1 = warp_colsum32(f, lane), s2 = warp_colsum32(sq, lane);
+              atomicAdd(stats + ncol0 + c0 + lane, s1);
+              atomicAdd(stats + P.ocols + ncol0 + c0 + lane, s2);
             }
           }
         }
       } else {
-        const int u = blockIdx.x * 2 + (r >> 6);
-        const bool live = u < P.total_slabs;
-        const TcTap tp = P.taps[live ? u / P.chunks : 0];
-        const long long kidx = (long long)tp.kidx * P.Cin + (u % P.chunks) * 64 + (r & 63);
-        const bool row_ok = live && kidx < P.kreal;
         float* dw = reinterpret_cast<float*>(out);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem + (uint32_t(q * 32) << 16) + c0, v);
-          tmem_ld_wait();
-          if (row_ok) {
+        for (int m = 0; m < MT; ++m) {
+          const int u = (mg * MT + m) * 2 + (r >> 6);
+          const bool live = u < P.total_slabs;
+          const TcTap tp = P.taps[live ? u / P.chunks : 0];
+          const long long kidx = (long long)tp.kidx * P.Cin + (u % P.chunks) * 64 + (r & 63);
+          const bool row_ok = live && kidx < P.kreal && have_acc && !P.debug_skip_epi;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            if (have_acc) {
+              tmem_ld32(acc + m * BN + c0, v);
+              tmem_ld_wait();
+            }
+            if (row_ok) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(dw + (long long)(ncol0 + c0 + i) * P.kreal + kidx, __uint_as_float(v[i]));
+              for (int i = 0; i < 32; ++i) atomicAdd(dw + (long long)(ncol0 + c0 + i) * P.kreal + kidx, __uint_as_float(v[i]));
+            }
           }
         }
+      }
+      if (have_acc) {
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[buf]);   // 128 arrivals release the accumulator buffer to the MMA issuer
+        ++seg;
       }
     }
   }
@@ -335,45 +498,95 @@ static Box choose_box(int target, int W, int H, int T, int B) {
   return best;
 }
 
-static int pick_bn(int cols, long long mtiles) {
-  // widest tile that still gives every SM work; columns must divide
-  int best = 64;
+// ---- tile shape selection -------------------------------------------------------------------------------------
+// A CTA tile is MT blocks of 128 accumulator rows x BN columns; one K step moves MT*16 KB of A and BN*128 B of B from L2
+// into shared memory and issues MT*4 MMAs (2*MT*BN tensor cycles).  The kernel is persistent (one CTA per SM), so the
+// cost of a shape is waves x (K steps x max(tensor cycles, bytes / L2 share)) — wide tiles raise FLOP/byte, small
+// tiles fill the machine when a layer has few pixels.
+struct TileCfg { int mt, bn, occ; };
+static int tc_env_int(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
+}
+static double step_cycles(int mt, int bn, long long active_ctas) {
+  const double chip_bw = 7400.0, sm_cap = 110.0;   // L2 -> SM bytes per cycle: whole chip (measured on these kernels), one SM
   const int sms = num_sms();
-  if (cols == 192) return 192;  // the 3-channel layers' (tap, ci) axis: one N tile, A read once
-  for (int bn = 256; bn >= 64; bn /= 2) {
+  double share = chip_bw / (double)(active_ctas < sms ? (active_ctas > 0 ? active_ctas : 1) : sms);
+  if (share > sm_cap) share = sm_cap;
+  const double bytes = mt * 16384.0 + bn * 128.0, mma = 2.0 * mt * bn;
+  const double ld = bytes / share;
+  return ld > mma ? ld : mma;
+}
+static TileCfg pick_tile(int mode, long long nboxes, int ncls, int cols, int nk) {
+  const int fm = tc_env_int("MCG_TC_MT"), fb = tc_env_int("MCG_TC_BN");
+  const int sms = num_sms();
+  TileCfg best{1, 64, 1};
+  double best_cost = 1e300;
+  const int bns[4] = {256, 192, 128, 64};
+  for (int bi = 0; bi < 4; ++bi) {
+    const int bn = bns[bi];
     if (cols % bn) continue;
-    long long ctas = mtiles * (cols / bn);
-    if (ctas >= sms || bn == 64) { best = bn; break; }
+    if (bn == 192 && mode != kFprop) continue;
+    if (fb && bn != fb && cols % fb == 0) continue;
+    for (int mt = 1; mt <= 4; ++mt) {
+      if (mt == 3 || (mt == 4 && bn != 64)) continue;
+      if (fm && mt != fm && !(fm == 4 && bn != 64 && mt == 2)) continue;
+      const long long units = (long long)ncls * (cols / bn) * nboxes;
+      const long long ctas = units < sms ? units : sms;
+      const long long upc = (units + ctas - 1) / ctas;
+      const long long full = upc / mt, rem = upc % mt;
+      const double cost = (double)nk * ((double)full * step_cycles(mt, bn, ctas) + (rem ? step_cycles((int)rem, bn, ctas) : 0.0)) +
+                          (double)(full + (rem ? 1 : 0)) * 300.0 + mt * bn * 6.0;
+      if (cost < best_cost) { best_cost = cost; best = TileCfg{mt, bn, 1}; }
+    }
   }
+  if (tc_env_int("MCG_TC_OCC") == 2 && best.mt <= 2 && best.bn != 192 && !(best.mt == 2 && best.bn == 256)) best.occ = 2;
   return best;
 }
+// cut `units` into equal contiguous ranges, one per CTA
+static int split_units(TcParams& P, long long units, long long min_per_cta, int occ = 1) {
+  const int sms = num_sms() * occ;
+  long long ctas = units / (min_per_cta > 0 ? min_per_cta : 1);
+  if (ctas > sms) ctas = sms;
+  if (ctas < 1) ctas = 1;
+  P.total_units = units;
+  P.units_per_cta = (units + ctas - 1) / ctas;
+  return (int)((units + P.units_per_cta - 1) / P.units_per_cta);
+}
 
-template <int MODE, int BN>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, dim3 grid, void* out, const float* bias,
-                     cudaStream_t st, const char* who) {
-  constexpr int STAGE = A_BYTES + BN * 128;
-  constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 3 : 4));  // BN<=128: ~96 KB so two CTAs share an SM
+template <int MODE, int BN, int MT, int OCC>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, int grid, void* out, const float* bias,
+                     float* stats, cudaStream_t st, const char* who) {
+  constexpr int STAGE = MT * A_BYTES + BN * 128;
+  constexpr int BUDGET = (OCC == 2 ? 110 : 220) * 1024;
+  constexpr int STAGES = (BUDGET / STAGE) > 8 ? 8 : (BUDGET / STAGE);
+  static_assert(STAGES >= 2, "ring too shallow");
   size_t smem = (size_t)STAGES * STAGE + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<MODE, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<MODE, BN, MT, STAGES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) MCG_FAIL((int)e, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
     configured = true;
   }
-  tc_conv_kernel<MODE, BN, STAGES><<<grid, kTcThreads, smem, st>>>(ma, mb, P, out, bias);
+  tc_conv_kernel<MODE, BN, MT, STAGES, OCC><<<grid, kTcThreads, smem, st>>>(ma, mb, P, out, bias, stats);
   MCG_CHECK_LAUNCH(who);
   return 0;
 }
 template <int MODE>
-static int launch_tc_bn(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, dim3 grid, void* out,
-                        const float* bias, cudaStream_t st, const char* who) {
-  switch (bn) {
-    case 64: return launch_tc<MODE, 64>(ma, mb, P, grid, out, bias, st, who);
-    case 128: return launch_tc<MODE, 128>(ma, mb, P, grid, out, bias, st, who);
-    case 192: return launch_tc<MODE, 192>(ma, mb, P, grid, out, bias, st, who);
-    case 256: return launch_tc<MODE, 256>(ma, mb, P, grid, out, bias, st, who);
-  }
-  MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: BN=%d", who, bn);
+static int launch_tc_cfg(TileCfg c, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, int grid, void* out,
+                         const float* bias, float* stats, cudaStream_t st, const char* who) {
+#define MCG_TC_CASE(bn_, mt_, occ_) \
+  if (c.bn == bn_ && c.mt == mt_ && c.occ == occ_) return launch_tc<MODE, bn_, mt_, occ_>(ma, mb, P, grid, out, bias, stats, st, who)
+  MCG_TC_CASE(64, 1, 1); MCG_TC_CASE(64, 2, 1);
+  MCG_TC_CASE(64, 1, 2); MCG_TC_CASE(64, 2, 2);
+  if (MODE != kWgrad) { MCG_TC_CASE(64, 4, 1); }
+  MCG_TC_CASE(128, 1, 1); MCG_TC_CASE(128, 2, 1);
+  MCG_TC_CASE(128, 1, 2); MCG_TC_CASE(128, 2, 2);
+  MCG_TC_CASE(256, 1, 1); MCG_TC_CASE(256, 2, 1);
+  MCG_TC_CASE(256, 1, 2);
+  if (MODE == kFprop) { MCG_TC_CASE(192, 1, 1); MCG_TC_CASE(192, 2, 1); }
+#undef MCG_TC_CASE
+  MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: tile %dx%d", who, c.mt * 128, c.bn);
 }
 
 bool tc_supported(const mcg_conv_geom* g) {
@@ -384,8 +597,9 @@ bool tc_supported(const mcg_conv_geom* g) {
   return true;
 }
 
+// stats: optional [2][ocols] fp32 accumulator (zeroed by the caller) that receives per-output-channel sum / sum of squares
 int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void* out, const float* bias, int out_dtype,
-            cudaStream_t st, int kreal = 0, int planar_chunk = 0, int planar_cols = 0) {
+            cudaStream_t st, int kreal = 0, int planar_chunk = 0, int planar_cols = 0, float* stats = nullptr) {
   const char* who = mode == kFprop ? "mcg_conv_fprop(tc)" : mode == kDgrad ? "mcg_conv_dgrad(tc)" : "mcg_conv_wgrad(tc)";
   if (!tc_supported(g)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: needs Cin,Cout %% 64 == 0, stride <= 2, <= 64 taps", who);
   TcParams P;
@@ -409,19 +623,22 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
     P.o_mul_w = P.o_mul_h = P.o_mul_t = 1;
     P.cls_w = P.cls_h = P.cls_t = 1;
     P.os_w = g->Cout; P.os_h = (long long)g->Wo * g->Cout; P.os_t = (long long)g->Ho * P.os_h; P.os_n = (long long)g->To * P.os_t;
+    P.ocols = g->Cout;
     P.chunks = g->Cin / 64;
     P.tap_begin[0] = 0; P.tap_count[0] = taps;
     for (int kt = 0, j = 0; kt < g->kT; ++kt)
       for (int kh = 0; kh < g->kH; ++kh)
         for (int kw = 0; kw < g->kW; ++kw, ++j) P.taps[j] = TcTap{(int16_t)kw, (int16_t)kh, (int16_t)kt, (int16_t)j};
     if ((rc = act_map(&ma, a, g->Cin, g->Wi, g->Hi, g->Ti, g->N, bx.w, bx.h, bx.t, bx.b, g->sW, g->sH, g->sT))) return rc;
-    long long mt = (long long)P.nbw * P.nbh * P.nbt * P.nbb;
-    int bn = pick_bn(g->Cout, mt);
+    P.nboxes = P.nbw * P.nbh * P.nbt * P.nbb;
+    const TileCfg cfg = pick_tile(kFprop, P.nboxes, 1, g->Cout, taps * P.chunks);
+    P.ntn = g->Cout / cfg.bn;
+    P.ntiles = P.ntn;
+    const int grid = split_units(P, (long long)P.ntiles * P.nboxes, 1, cfg.occ);
     uint64_t d2[2] = {(uint64_t)P.Ktot, (uint64_t)g->Cout}, s2[1] = {(uint64_t)P.Ktot * 2};
-    uint32_t b2[2] = {64, (uint32_t)bn}, e2[2] = {1, 1};
+    uint32_t b2[2] = {64, (uint32_t)cfg.bn}, e2[2] = {1, 1};
     if ((rc = get_map(&mb, b, 2, d2, s2, b2, e2))) return rc;
-    dim3 grid((unsigned)mt, (unsigned)(g->Cout / bn), 1);
-    return launch_tc_bn<kFprop>(bn, ma, mb, P, grid, out, bias, st, who);
+    return launch_tc_cfg<kFprop>(cfg, ma, mb, P, grid, out, bias, stats, st, who);
   }
   if (mode == kDgrad) {
     // a = dy (N,To,Ho,Wo,Cout), b = w bf16, out = dx (N,Ti,Hi,Wi,Cin); one class per residue of the input coordinate
@@ -436,8 +653,9 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
     P.o_mul_w = cw; P.o_mul_h = ch; P.o_mul_t = ct;
     P.cls_w = cw; P.cls_h = ch; P.cls_t = ct;
     P.os_w = g->Cin; P.os_h = (long long)g->Wi * g->Cin; P.os_t = (long long)g->Hi * P.os_h; P.os_n = (long long)g->Ti * P.os_t;
+    P.ocols = g->Cin;
     P.chunks = g->Cout / 64;
-    int ncls = cw * ch * ct, j = 0;
+    int ncls = cw * ch * ct, j = 0, max_taps = 0;
     for (int c = 0; c < ncls; ++c) {
       const int pw = c % cw, ph = (c / cw) % ch, pt = c / (cw * ch);
       P.tap_begin[c] = j;
@@ -455,15 +673,18 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
         }
       }
       P.tap_count[c] = j - P.tap_begin[c];
+      if (P.tap_count[c] > max_taps) max_taps = P.tap_count[c];
     }
     if ((rc = act_map(&ma, a, g->Cout, g->Wo, g->Ho, g->To, g->N, bx.w, bx.h, bx.t, bx.b, 1, 1, 1))) return rc;
-    long long mt = (long long)P.nbw * P.nbh * P.nbt * P.nbb * ncls;
-    int bn = pick_bn(g->Cin, mt);
+    P.nboxes = P.nbw * P.nbh * P.nbt * P.nbb;
+    const TileCfg cfg = pick_tile(kDgrad, P.nboxes, ncls, g->Cin, max_taps * P.chunks);
+    P.ntn = g->Cin / cfg.bn;
+    P.ntiles = ncls * P.ntn;
+    const int grid = split_units(P, (long long)P.ntiles * P.nboxes, 1, cfg.occ);
     uint64_t d2[2] = {(uint64_t)P.Ktot, (uint64_t)g->Cout}, s2[1] = {(uint64_t)P.Ktot * 2};
     uint32_t b2[2] = {64, 64}, e2[2] = {1, 1};
     if ((rc = get_map(&mb, b, 2, d2, s2, b2, e2))) return rc;
-    dim3 grid((unsigned)mt, (unsigned)(g->Cin / bn), 1);
-    return launch_tc_bn<kDgrad>(bn, ma, mb, P, grid, out, bias, st, who);
+    return launch_tc_cfg<kDgrad>(cfg, ma, mb, P, grid, out, bias, stats, st, who);
   }
   // ---- wgrad: a = x (N,Ti,Hi,Wi,Cin), b = dy (N,To,Ho,Wo,Cout), out = dw fp32 (Cout, taps*Cin), accumulated
   {
@@ -476,27 +697,25 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
       for (int kh = 0; kh < g->kH; ++kh)
         for (int kw = 0; kw < g->kW; ++kw, ++j) P.taps[j] = TcTap{(int16_t)kw, (int16_t)kh, (int16_t)kt, (int16_t)j};
     const int slabs = taps * P.chunks;
-    const int mtiles = (slabs + 1) / 2;   // an odd count leaves one zero-filled dummy slab in the last tile
     P.total_slabs = slabs;
     P.kreal = kreal > 0 ? kreal : P.Ktot;
-    int bn = 64;
-    for (int c = 256; c >= 64; c /= 2)
-      if (g->Cout % c == 0) { bn = c; break; }
+    P.debug_skip_epi = tc_env_int("MCG_TC_DEBUG_NOEPI");
     P.total_boxes = P.nbw * P.nbh * P.nbt * P.nbb;
-    long long tiles = (long long)mtiles * (g->Cout / bn);
-    // one full wave: resident CTAs per SM is 2 for BN <= 128 (96 KB of stages), 1 for BN = 256; rounding the split
-    // count UP spills a few CTAs into a second wave that doubles the kernel time (ncu: Dv.dc2, 320 CTAs on 296 slots)
-    const long long slots = (long long)num_sms() * (bn <= 128 ? 2 : 1);
-    long long want = slots / tiles;
-    long long maxs = ceil_div(P.total_boxes, 8);
-    int splits = (int)(want < maxs ? want : maxs);
-    if (splits < 1) splits = 1;
-    P.boxes_per_split = ceil_div(P.total_boxes, splits);
-    splits = ceil_div(P.total_boxes, P.boxes_per_split);
+    // widest tile the channel counts allow: B (dy) is re-read once per row group, A (x) once per column tile, and the
+    // fp32 red.add volume grows with the number of K splits, so few large tiles win; stream-K keeps every SM busy.
+    TileCfg cfg{slabs >= 4 ? 2 : 1, 64, 1};
+    for (int c = 256; c >= 64; c /= 2)
+      if (g->Cout % c == 0) { cfg.bn = c; break; }
+    if (tc_env_int("MCG_TC_WMT")) cfg.mt = tc_env_int("MCG_TC_WMT");
+    if (tc_env_int("MCG_TC_WBN") && g->Cout % tc_env_int("MCG_TC_WBN") == 0) cfg.bn = tc_env_int("MCG_TC_WBN");
+    const int mgroups = ceil_div(slabs, 2 * cfg.mt);
+    P.ntn = g->Cout / cfg.bn;
+    P.ntiles = mgroups * P.ntn;
+    if (tc_env_int("MCG_TC_OCC") == 2 && !(cfg.bn == 256 && cfg.mt == 2)) cfg.occ = 2;
+    const int ctas = split_units(P, (long long)P.ntiles * P.total_boxes, 8, cfg.occ);   // at least 8 K steps per CTA
     if ((rc = act_map(&ma, a, g->Cin, g->Wi, g->Hi, g->Ti, g->N, bx.w, bx.h, bx.t, bx.b, g->sW, g->sH, g->sT))) return rc;
     if ((rc = act_map(&mb, b, g->Cout, g->Wo, g->Ho, g->To, g->N, bx.w, bx.h, bx.t, bx.b, 1, 1, 1))) return rc;
-    dim3 grid((unsigned)mtiles, (unsigned)(g->Cout / bn), (unsigned)splits);
-    return launch_tc_bn<kWgrad>(bn, ma, mb, P, grid, out, nullptr, st, who);
+    return launch_tc_cfg<kWgrad>(cfg, ma, mb, P, ctas, out, nullptr, nullptr, st, who);
   }
 }
 
