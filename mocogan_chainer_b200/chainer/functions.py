@@ -127,7 +127,9 @@ class ConvolutionND(FunctionNode):
         x, W, b = inputs
         nd = _nd_of(x)
         self.nd = nd
-        xdt = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else act_dtype()
+        # bf16 mode: every convolution reads bf16 activations (the generator's fp32 latent z included), so gradients
+        # flowing back never need a dtype conversion pass
+        xdt = act_dtype() if config.compute_dtype == "bf16" else (x.dtype if x.dtype in (torch.float32, torch.bfloat16) else act_dtype())
         xp = as_physical(x, xdt)
         N, T, H, Wd, Cx = xp.shape
         ish = W.internal_shape  # (Cout_c, *k, Cin_c)

@@ -146,74 +146,151 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(Geo g, const T* __restri
 // generator's first deconvolution (net.py:44,137,178).  They are plain GEMMs over contiguous rows:
 //   fprop : y[m][col] = bias[col] + sum_k x[m][k] * w[col][k]          (M = batch, K = taps*Cin)
 //   dgrad : dx[m][k]  = bias[k % Cin] + sum_co dy[m][co] * w[co][k]
-template <typename T>
+// y[m][col] = bias[col] + sum_k x[m][k] * w[col][k]: a block owns RM rows x CPB columns, so every weight row is read
+// once per RM rows and every x row once per CPB columns (the one-row version re-read all of w for each row: G.dc1's
+// backward-data moved 1.1 GB through L2 for 0.55 GFLOP).
+template <typename T, int RM, int CPB>
 __global__ void __launch_bounds__(256) fullwin_fprop_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ bias, void* __restrict__ y,
-                                                            int out_bf16, int M, int Ncols, int K, int cols_per_block) {
-  __shared__ float red[8];
-  const int m = blockIdx.x;
-  const T* xr = x + (long long)m * K;
-  for (int cc = 0; cc < cols_per_block; ++cc) {
-    const int col = blockIdx.y * cols_per_block + cc;
-    if (col >= Ncols) break;
-    const float* wr = w + (long long)col * K;
-    float acc = 0.f;
-    if ((K & 7) == 0) {
-      for (int k = threadIdx.x * 8; k < K; k += 256 * 8) {
-        float xv[8], wv[8];
-        ld8<T>(xr + k, xv);
-        ld8<float>(wr + k, wv);
+                                                            int out_bf16, int M, int Ncols, int K) {
+  __shared__ float red[8][RM * CPB];
+  const int m0 = blockIdx.x * RM, c0 = blockIdx.y * CPB;
+  float acc[RM][CPB];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fmaf(xv[i], wv[i], acc);
+  for (int r = 0; r < RM; ++r)
+#pragma unroll
+    for (int c = 0; c < CPB; ++c) acc[r][c] = 0.f;
+  if ((K & 7) == 0) {
+    for (int k = threadIdx.x * 8; k < K; k += 256 * 8) {
+      float wv[CPB][8];
+#pragma unroll
+      for (int c = 0; c < CPB; ++c) {
+        if (c0 + c < Ncols) ld8<float>(w + (long long)(c0 + c) * K + k, wv[c]);
+        else
+#pragma unroll
+          for (int i = 0; i < 8; ++i) wv[c][i] = 0.f;
       }
-    } else {
-      for (int k = threadIdx.x; k < K; k += 256) acc = fmaf(ld<T>(xr, k), wr[k], acc);
+#pragma unroll
+      for (int r = 0; r < RM; ++r) {
+        if (m0 + r >= M) break;
+        float xv[8];
+        ld8<T>(x + (long long)(m0 + r) * K + k, xv);
+#pragma unroll
+        for (int c = 0; c < CPB; ++c)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[r][c] = fmaf(xv[i], wv[c][i], acc[r][c]);
+      }
     }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float s = 0.f;
-      for (int i = 0; i < 8; ++i) s += red[i];
-      if (bias) s += bias[col];
-      const long long o = (long long)m * Ncols + col;
-      if (out_bf16) reinterpret_cast<__nv_bfloat16*>(y)[o] = __float2bfloat16_rn(s);
-      else reinterpret_cast<float*>(y)[o] = s;
+  } else {
+    for (int k = threadIdx.x; k < K; k += 256)
+#pragma unroll
+      for (int r = 0; r < RM; ++r) {
+        if (m0 + r >= M) break;
+        const float xv = ld<T>(x, (long long)(m0 + r) * K + k);
+#pragma unroll
+        for (int c = 0; c < CPB; ++c)
+          if (c0 + c < Ncols) acc[r][c] = fmaf(xv, w[(long long)(c0 + c) * K + k], acc[r][c]);
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < RM; ++r)
+#pragma unroll
+    for (int c = 0; c < CPB; ++c) {
+      float v = acc[r][c];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][r * CPB + c] = v;
     }
-    __syncthreads();
+  __syncthreads();
+  if (threadIdx.x < RM * CPB) {
+    const int r = threadIdx.x / CPB, c = threadIdx.x % CPB;
+    if (m0 + r < M && c0 + c < Ncols) {
+      float sres = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sres += red[i][threadIdx.x];
+      if (bias) sres += bias[c0 + c];
+      const long long o = (long long)(m0 + r) * Ncols + c0 + c;
+      if (out_bf16) reinterpret_cast<__nv_bfloat16*>(y)[o] = __float2bfloat16_rn(sres);
+      else reinterpret_cast<float*>(y)[o] = sres;
+    }
   }
 }
 
-template <typename T>
+// dx[m][k] = bias[k % Cin] + sum_co dy[m][co] * w[co][k]: a thread owns four consecutive k of RM rows, so each 16-byte
+// weight vector is loaded once per RM rows (K % 4 == 0 is checked by the launcher; Cin % 4 == 0 keeps a quad inside one
+// pixel).  The dy values are warp-uniform broadcasts.
+template <typename T, int RM>
 __global__ void __launch_bounds__(256) fullwin_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w,
                                                             const float* __restrict__ bias, void* __restrict__ dx,
                                                             int out_bf16, int accumulate, int M, int Cout, int K, int Cin) {
-  // four consecutive k per thread (K % 4 == 0 is checked by the launcher; Cin % 4 == 0 keeps a quad inside one pixel)
-  const long long quads = (long long)M * (K / 4);
+  const int kq = K / 4;
+  const long long quads = (long long)((M + RM - 1) / RM) * kq;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
-    const int m = (int)(q / (K / 4)), k = (int)(q % (K / 4)) * 4;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    if (bias) { a0 = bias[k % Cin]; a1 = bias[(k + 1) % Cin]; a2 = bias[(k + 2) % Cin]; a3 = bias[(k + 3) % Cin]; }
-    const T* dr = dy + (long long)m * Cout;
+    const int m0 = (int)(q / kq) * RM, k = (int)(q % kq) * 4;
+    float a[RM][4];
+    const float b0 = bias ? bias[k % Cin] : 0.f, b1 = bias ? bias[(k + 1) % Cin] : 0.f, b2 = bias ? bias[(k + 2) % Cin] : 0.f,
+                b3 = bias ? bias[(k + 3) % Cin] : 0.f;
+#pragma unroll
+    for (int r = 0; r < RM; ++r) { a[r][0] = b0; a[r][1] = b1; a[r][2] = b2; a[r][3] = b3; }
     for (int co = 0; co < Cout; ++co) {
-      const float d = ld<T>(dr, co);
       const float4 wv = *reinterpret_cast<const float4*>(w + (long long)co * K + k);
-      a0 = fmaf(d, wv.x, a0); a1 = fmaf(d, wv.y, a1); a2 = fmaf(d, wv.z, a2); a3 = fmaf(d, wv.w, a3);
+#pragma unroll
+      for (int r = 0; r < RM; ++r) {
+        const float d = (m0 + r < M) ? ld<T>(dy, (long long)(m0 + r) * Cout + co) : 0.f;
+        a[r][0] = fmaf(d, wv.x, a[r][0]); a[r][1] = fmaf(d, wv.y, a[r][1]);
+        a[r][2] = fmaf(d, wv.z, a[r][2]); a[r][3] = fmaf(d, wv.w, a[r][3]);
+      }
     }
-    const long long o = (long long)m * K + k;
-    if (out_bf16) {
-      __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(dx) + o;
-      if (accumulate) { a0 += __bfloat162float(p[0]); a1 += __bfloat162float(p[1]); a2 += __bfloat162float(p[2]); a3 += __bfloat162float(p[3]); }
-      __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&lo);
-      u.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(p) = u;
-    } else {
-      float* p = reinterpret_cast<float*>(dx) + o;
-      if (accumulate) { a0 += p[0]; a1 += p[1]; a2 += p[2]; a3 += p[3]; }
-      *reinterpret_cast<float4*>(p) = make_float4(a0, a1, a2, a3);
+#pragma unroll
+    for (int r = 0; r < RM; ++r) {
+      if (m0 + r >= M) break;
+      const long long o = (long long)(m0 + r) * K + k;
+      float a0 = a[r][0], a1 = a[r][1], a2 = a[r][2], a3 = a[r][3];
+      if (out_bf16) {
+        __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(dx) + o;
+        if (accumulate) { a0 += __bfloat162float(p[0]); a1 += __bfloat162float(p[1]); a2 += __bfloat162float(p[2]); a3 += __bfloat162float(p[3]); }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&lo);
+        u.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(p) = u;
+      } else {
+        float* p = reinterpret_cast<float*>(dx) + o;
+        if (accumulate) { a0 += p[0]; a1 += p[1]; a2 += p[2]; a3 += p[3]; }
+        *reinterpret_cast<float4*>(p) = make_float4(a0, a1, a2, a3);
+      }
     }
+  }
+}
+
+// dw[co][k] += sum_m dy[m][co] * x[m][k] for a full-window layer (x[m] is one contiguous row of K values): a thread owns
+// four consecutive k for CB output channels, rows are split over blockIdx.z and meet in fp32 red.add (wgrad accumulates).
+template <typename T, int CB>
+__global__ void __launch_bounds__(256) fullwin_wgrad_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                            float* __restrict__ dw, int M, int Cout, int K, int rows_per_split) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= K / 4) return;
+  const int k = q * 4, co0 = blockIdx.y * CB;
+  const int m_begin = blockIdx.z * rows_per_split;
+  int m_end = m_begin + rows_per_split;
+  if (m_end > M) m_end = M;
+  float acc[CB][4];
+#pragma unroll
+  for (int c = 0; c < CB; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+  for (int m = m_begin; m < m_end; ++m) {
+    const T* xr = x + (long long)m * K + k;
+    const float x0 = ld<T>(xr, 0), x1 = ld<T>(xr, 1), x2 = ld<T>(xr, 2), x3 = ld<T>(xr, 3);
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      const float d = (co0 + c < Cout) ? ld<T>(dy, (long long)m * Cout + co0 + c) : 0.f;
+      acc[c][0] = fmaf(d, x0, acc[c][0]); acc[c][1] = fmaf(d, x1, acc[c][1]);
+      acc[c][2] = fmaf(d, x2, acc[c][2]); acc[c][3] = fmaf(d, x3, acc[c][3]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CB; ++c) {
+    if (co0 + c >= Cout) break;
+    float* o = dw + (long long)(co0 + c) * K + k;
+    atomicAdd(o, acc[c][0]); atomicAdd(o + 1, acc[c][1]); atomicAdd(o + 2, acc[c][2]); atomicAdd(o + 3, acc[c][3]);
   }
 }
 
@@ -251,17 +328,44 @@ int simt_conv(int mode, const mcg_conv_geom* c, const void* a, const void* b_act
   if (!no_fullwin && is_full_window(g) && mode != kWgrad && (mode == kFprop || g.K % 4 == 0)) {
     const int ob = out_dtype == MCG_BF16;
     if (mode == kFprop) {
-      int cpb = g.Cout >= 16 ? 4 : 1;
-      dim3 grid((unsigned)g.N, (unsigned)((g.Cout + cpb - 1) / cpb));
-      if (dtype == MCG_F32) fullwin_fprop_kernel<float><<<grid, 256, 0, st>>>((const float*)a, w, bias, out, ob, g.N, g.Cout, g.K, cpb);
-      else fullwin_fprop_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, w, bias, out, ob, g.N, g.Cout, g.K, cpb);
+      if (g.Cout >= 16) {   // wide output (G.dc1 backward-data): 8 rows x 4 columns per block
+        dim3 grid((unsigned)((g.N + 7) / 8), (unsigned)((g.Cout + 3) / 4));
+        if (dtype == MCG_F32) fullwin_fprop_kernel<float, 8, 4><<<grid, 256, 0, st>>>((const float*)a, w, bias, out, ob, g.N, g.Cout, g.K);
+        else fullwin_fprop_kernel<__nv_bfloat16, 8, 4><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, w, bias, out, ob, g.N, g.Cout, g.K);
+      } else {              // a handful of columns (the discriminators' last layer): one row per block keeps the grid full
+        dim3 grid((unsigned)g.N, (unsigned)g.Cout);
+        if (dtype == MCG_F32) fullwin_fprop_kernel<float, 1, 1><<<grid, 256, 0, st>>>((const float*)a, w, bias, out, ob, g.N, g.Cout, g.K);
+        else fullwin_fprop_kernel<__nv_bfloat16, 1, 1><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, w, bias, out, ob, g.N, g.Cout, g.K);
+      }
     } else {
-      long long total = (long long)g.N * (g.K / 4);
+      const int rm = g.N >= 256 ? 8 : 1;   // many rows (G.dc1 forward): share each weight vector between 8 of them
+      long long total = (long long)((g.N + rm - 1) / rm) * (g.K / 4);
       long long nb = (total + 255) / 256;
       int blocks = (int)(nb < (long long)num_sms() * 16 ? nb : (long long)num_sms() * 16);
-      if (dtype == MCG_F32) fullwin_dgrad_kernel<float><<<blocks, 256, 0, st>>>((const float*)a, w, bias, out, ob, accumulate, g.N, g.Cout, g.K, g.Cin);
-      else fullwin_dgrad_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)a, w, bias, out, ob, accumulate, g.N, g.Cout, g.K, g.Cin);
+#define GO_FW(T, RM_) fullwin_dgrad_kernel<T, RM_><<<blocks, 256, 0, st>>>((const T*)a, w, bias, out, ob, accumulate, g.N, g.Cout, g.K, g.Cin)
+      if (dtype == MCG_F32) { if (rm == 8) GO_FW(float, 8); else GO_FW(float, 1); }
+      else { if (rm == 8) GO_FW(__nv_bfloat16, 8); else GO_FW(__nv_bfloat16, 1); }
+#undef GO_FW
     }
+    MCG_CHECK_LAUNCH(who);
+    return 0;
+  }
+  if (!no_fullwin && is_full_window(g) && mode == kWgrad && g.K % 4 == 0) {
+    // a = dy (N, Cout), b_act = x (N, K)
+    const int quads = g.K / 4;
+    const int cb = g.Cout >= 8 ? 8 : 1;
+    const int gy = (g.Cout + cb - 1) / cb;
+    long long ctas = (long long)((quads + 255) / 256) * gy;
+    int splits = (int)((4LL * num_sms() + ctas - 1) / ctas);
+    if (splits > (g.N + 7) / 8) splits = (g.N + 7) / 8;   // at least 8 rows per split
+    if (splits < 1) splits = 1;
+    const int rps = (g.N + splits - 1) / splits;
+    splits = (g.N + rps - 1) / rps;
+    dim3 grid((unsigned)((quads + 255) / 256), (unsigned)gy, (unsigned)splits);
+#define GO_WG(T, CB_) fullwin_wgrad_kernel<T, CB_><<<grid, 256, 0, st>>>((const T*)a, (const T*)b_act, (float*)out, g.N, g.Cout, g.K, rps)
+    if (dtype == MCG_F32) { if (cb == 8) GO_WG(float, 8); else GO_WG(float, 1); }
+    else { if (cb == 8) GO_WG(__nv_bfloat16, 8); else GO_WG(__nv_bfloat16, 1); }
+#undef GO_WG
     MCG_CHECK_LAUNCH(who);
     return 0;
   }

@@ -785,23 +785,31 @@ __global__ void __launch_bounds__(128) im2col_line_kernel(const __nv_bfloat16* _
     }
   }
   __syncthreads();
-  const int vec_per_row = Kp / 8;
+  // Each thread owns ONE 16-byte column group (8 consecutive k) and walks the output pixels of the line, so the
+  // k -> (run, tap, channel) decode is done once; consecutive threads write consecutive 16-byte vectors.
+  const int vpr = Kp / 8;                 // vectors per cols row
+  const int wq_n = blockDim.x / vpr;      // pixels in flight per pass
+  const int kv = threadIdx.x % vpr, wq = threadIdx.x / vpr;
+  if (wq >= wq_n) return;
+  int off[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = kv * 8 + i;
+    off[i] = k < K ? (k / (KW * CIN)) * L + k % (KW * CIN) : -1;
+  }
   const long long m0 = ((n * To + to) * Ho + ho) * (long long)Wo;
   uint4* dst = reinterpret_cast<uint4*>(cols + m0 * Kp);
-  for (int v = threadIdx.x; v < Wo * vec_per_row; v += blockDim.x) {
-    const int wo = v / vec_per_row, k0 = (v % vec_per_row) * 8;
-    __align__(16) unsigned short o[8];
+  const int step = sW * CIN;
+  for (int wo = wq; wo < Wo; wo += wq_n) {
+    const int base = wo * step;
+    uint32_t o[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = k0 + i;
-      unsigned short val = 0;
-      if (k < K) {
-        const int run = k / (KW * CIN), rem = k % (KW * CIN);
-        val = rows[run * L + wo * sW * CIN + rem];
-      }
-      o[i] = val;
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t lo = off[2 * i] >= 0 ? rows[off[2 * i] + base] : 0u;
+      const uint32_t hi = off[2 * i + 1] >= 0 ? rows[off[2 * i + 1] + base] : 0u;
+      o[i] = lo | (hi << 16);
     }
-    dst[v] = *reinterpret_cast<const uint4*>(o);
+    dst[wo * vpr + kv] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 // wp[co][Kp] = w[co][k] (k < K) else 0
@@ -826,7 +834,7 @@ __global__ void __launch_bounds__(128) col2im_line_kernel(const __nv_bfloat16* _
                                                           void* __restrict__ dx, int out_f32, long long Mpix, int Cin, int Ti, int Hi,
                                                           int Wi, int To, int Ho, int Wo, int kT, int kH, int kW, int sT, int sH,
                                                           int sW, int pT, int pH, int pW) {
-  extern __shared__ unsigned short zs[];  // [valid runs][Wo][kW*Cin]
+  extern __shared__ __align__(16) unsigned short zs[];  // [valid runs][Wo][kW*Cin]
   __shared__ int run_row[64], run_col[64];
   __shared__ int nvalid;
   const int RUN = kW * Cin;
@@ -852,12 +860,23 @@ __global__ void __launch_bounds__(128) col2im_line_kernel(const __nv_bfloat16* _
   __syncthreads();
   const int nv = nvalid;
   // Z is planar: Z[run][pixel][RUN]; a line needs, per valid run, Wo*RUN contiguous elements
-  const uint32_t* zsrc = reinterpret_cast<const uint32_t*>(Z);
-  uint32_t* zs32 = reinterpret_cast<uint32_t*>(zs);
-  const int words = Wo * RUN / 2;
-  for (int v = 0; v < nv; ++v) {
-    const long long base = ((long long)run_col[v] * Mpix + (long long)run_row[v] * Wo) * RUN / 2;
-    for (int e = threadIdx.x; e < words; e += blockDim.x) zs32[v * words + e] = __ldg(zsrc + base + e);
+  if ((Wo * RUN) % 8 == 0) {   // 16-byte copies, all runs of the line in flight together
+    const uint4* zsrc = reinterpret_cast<const uint4*>(Z);
+    uint4* zs128 = reinterpret_cast<uint4*>(zs);
+    const int vecs = Wo * RUN / 8;
+    for (int e = threadIdx.x; e < nv * vecs; e += blockDim.x) {
+      const int v = e / vecs, i = e - v * vecs;
+      const long long base = ((long long)run_col[v] * Mpix + (long long)run_row[v] * Wo) * RUN / 8;
+      zs128[e] = __ldg(zsrc + base + i);
+    }
+  } else {
+    const uint32_t* zsrc = reinterpret_cast<const uint32_t*>(Z);
+    uint32_t* zs32 = reinterpret_cast<uint32_t*>(zs);
+    const int words = Wo * RUN / 2;
+    for (int v = 0; v < nv; ++v) {
+      const long long base = ((long long)run_col[v] * Mpix + (long long)run_row[v] * Wo) * RUN / 2;
+      for (int e = threadIdx.x; e < words; e += blockDim.x) zs32[v * words + e] = __ldg(zsrc + base + e);
+    }
   }
   __syncthreads();
   const long long obase = ((n * Ti + ti) * Hi + hi) * (long long)Wi * Cin;
