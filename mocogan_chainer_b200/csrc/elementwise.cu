@@ -27,9 +27,13 @@ static int pow2_ge(int x) {
   return p;
 }
 
+// Reduction functors.  `prep` loads the per-channel constants of the thread's channel group ONCE (a thread keeps the
+// same channels for every row it visits); `operator()` then touches only the streamed tensors.
 struct StatsF {  // sum y, sum y^2
+  template <int VEC> struct Regs {};
+  template <int VEC> __device__ __forceinline__ void prep(int, Regs<VEC>&) const {}
   template <typename T, int VEC>
-  __device__ __forceinline__ void operator()(const T* y, const T*, long long off, int c0, float (&a)[VEC],
+  __device__ __forceinline__ void operator()(const T* y, const T*, long long off, const Regs<VEC>&, float (&a)[VEC],
                                              float (&b)[VEC]) const {
     float v[VEC];
     if (VEC == 8) ld8<T>(y + off, reinterpret_cast<float(&)[8]>(v));
@@ -39,8 +43,10 @@ struct StatsF {  // sum y, sum y^2
   }
 };
 struct SumF {  // sum g
+  template <int VEC> struct Regs {};
+  template <int VEC> __device__ __forceinline__ void prep(int, Regs<VEC>&) const {}
   template <typename T, int VEC>
-  __device__ __forceinline__ void operator()(const T* g, const T*, long long off, int c0, float (&a)[VEC],
+  __device__ __forceinline__ void operator()(const T* g, const T*, long long off, const Regs<VEC>&, float (&a)[VEC],
                                              float (&b)[VEC]) const {
     float v[VEC];
     if (VEC == 8) ld8<T>(g + off, reinterpret_cast<float(&)[8]>(v));
@@ -53,8 +59,15 @@ struct BnBwdF {  // sum g', sum g'*xhat with g' = g * act'(scale*y+shift)
   const float *mean, *invstd, *scale, *shift;
   int act;
   float slope;
+  template <int VEC> struct Regs { float mean[VEC], invstd[VEC], scale[VEC], shift[VEC]; };
+  template <int VEC> __device__ __forceinline__ void prep(int c0, Regs<VEC>& r) const {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      r.mean[i] = mean[c0 + i]; r.invstd[i] = invstd[c0 + i]; r.scale[i] = scale[c0 + i]; r.shift[i] = shift[c0 + i];
+    }
+  }
   template <typename T, int VEC>
-  __device__ __forceinline__ void operator()(const T* g, const T* y, long long off, int c0, float (&a)[VEC],
+  __device__ __forceinline__ void operator()(const T* g, const T* y, long long off, const Regs<VEC>& r, float (&a)[VEC],
                                              float (&b)[VEC]) const {
     float gv[VEC], yv[VEC];
     if (VEC == 8) {
@@ -66,11 +79,10 @@ struct BnBwdF {  // sum g', sum g'*xhat with g' = g * act'(scale*y+shift)
     }
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      int c = c0 + i;
-      float pre = scale[c] * yv[i] + shift[c];
+      float pre = r.scale[i] * yv[i] + r.shift[i];
       float gp = gv[i] * act_grad(act, slope, pre, 0);
       a[i] += gp;
-      b[i] += gp * (yv[i] - mean[c]) * invstd[c];
+      b[i] += gp * (yv[i] - r.mean[i]) * r.invstd[i];
     }
   }
 };
@@ -86,8 +98,20 @@ __global__ void __launch_bounds__(kRedThreads) colreduce_kernel(F f, const T* p0
 #pragma unroll
   for (int i = 0; i < VEC; ++i) a[i] = b[i] = 0.f;
   if (tx < CG) {
-    for (long long m = (long long)blockIdx.x * rpb + ty; m < M; m += (long long)gridDim.x * rpb)
-      f.template operator()<T, VEC>(p0, p1, m * C + (long long)tx * VEC, tx * VEC, a, b);
+    typename F::template Regs<VEC> regs;
+    f.template prep<VEC>(tx * VEC, regs);
+    const long long step = (long long)gridDim.x * rpb;
+    long long m = (long long)blockIdx.x * rpb + ty;
+    float a2[VEC], b2[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) a2[i] = b2[i] = 0.f;
+    for (; m + step < M; m += 2 * step) {   // two independent rows in flight per thread
+      f.template operator()<T, VEC>(p0, p1, m * C + (long long)tx * VEC, regs, a, b);
+      f.template operator()<T, VEC>(p0, p1, (m + step) * C + (long long)tx * VEC, regs, a2, b2);
+    }
+    if (m < M) f.template operator()<T, VEC>(p0, p1, m * C + (long long)tx * VEC, regs, a, b);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { a[i] += a2[i]; b[i] += b2[i]; }
   }
   float* mine = red + ((size_t)ty * tpr + tx) * 2 * VEC;
 #pragma unroll
@@ -194,7 +218,9 @@ __global__ void __launch_bounds__(256) sum2_finalize(const float* partial, int n
 // =====================================================================================================
 // affine + activation + noise
 // =====================================================================================================
-template <typename TI, typename TO, int VEC>
+// VEC == 8 with FIXED: the launcher made (gridDim.x * 256) a multiple of C/8, so a thread keeps one channel group for all
+// of its rows: scale/shift live in registers and the row index advances without a division.
+template <typename TI, typename TO, int VEC, bool FIXED>
 __global__ void __launch_bounds__(256) affine_act_noise_kernel(
     const TI* __restrict__ y, long long M, int C, long long P, const float* __restrict__ scale,
     const float* __restrict__ shift, int act, float slope, float sigma, const float* __restrict__ noise,
@@ -202,16 +228,25 @@ __global__ void __launch_bounds__(256) affine_act_noise_kernel(
     TO* __restrict__ out) {
   const int CG = C / VEC;
   const long long total = M * CG;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    long long m = idx / CG;
-    int c0 = (int)(idx % CG) * VEC;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float sc[VEC], sh[VEC];
+  int c0 = (int)(idx % CG) * VEC;
+  long long m = idx / CG;
+  const long long mstep = stride / CG;
+  if (FIXED && scale) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { sc[i] = scale[c0 + i]; sh[i] = shift[c0 + i]; }
+  }
+  for (; idx < total; idx += stride) {
+    if (!FIXED) { m = idx / CG; c0 = (int)(idx % CG) * VEC; }
     float v[VEC];
     if (VEC == 8) ld8<TI>(y + m * C + c0, reinterpret_cast<float(&)[8]>(v));
     else v[0] = ld<TI>(y, m * C + c0);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      float pre = scale ? scale[c0 + i] * v[i] + shift[c0 + i] : v[i];
+      float pre = v[i];
+      if (scale) pre = FIXED ? sc[i] * v[i] + sh[i] : scale[c0 + i] * v[i] + shift[c0 + i];
       v[i] = act_fwd(act, slope, pre);
     }
     if (noise) {
@@ -235,6 +270,7 @@ __global__ void __launch_bounds__(256) affine_act_noise_kernel(
     }
     if (VEC == 8) st8<TO>(out + m * C + c0, reinterpret_cast<const float(&)[8]>(v));
     else st<TO>(out, m * C + c0, v[0]);
+    if (FIXED) m += mstep;
   }
 }
 
@@ -296,7 +332,10 @@ __global__ void __launch_bounds__(256) pack_elem_kernel(const TI* __restrict__ s
 // =====================================================================================================
 // backward of (BN ->) activation, apply half
 // =====================================================================================================
-template <typename TI, typename TO, int VEC>
+// With BN:  gy = gamma*invstd*(g' - (xhat*dgamma + dbeta)/M) = A*(g' - ((y - mean)*B + D))  with per-channel A = gamma*invstd,
+// B = invstd*dgamma/M, D = dbeta/M.  FIXED (see affine_act_noise_kernel) keeps A, B, D, mean and the activation's
+// scale/shift in registers.
+template <typename TI, typename TO, int VEC, bool FIXED>
 __global__ void __launch_bounds__(256) act_bn_bwd_apply_kernel(
     const TI* __restrict__ g, const TI* __restrict__ y, long long M, int C, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ scale,
@@ -304,10 +343,25 @@ __global__ void __launch_bounds__(256) act_bn_bwd_apply_kernel(
     const float* __restrict__ dbeta, float inv_m, TO* __restrict__ gy) {
   const int CG = C / VEC;
   const long long total = M * CG;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    long long m = idx / CG;
-    int c0 = (int)(idx % CG) * VEC;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int c0 = (int)(idx % CG) * VEC;
+  long long m = idx / CG;
+  const long long mstep = stride / CG;
+  float cA[VEC], cB[VEC], cD[VEC], cM[VEC], sc[VEC], sh[VEC];
+  if (FIXED && mean) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c = c0 + i;
+      cA[i] = gamma[c] * invstd[c];
+      cB[i] = invstd[c] * dgamma[c] * inv_m;
+      cD[i] = dbeta[c] * inv_m;
+      cM[i] = mean[c];
+      sc[i] = scale[c]; sh[i] = shift[c];
+    }
+  }
+  for (; idx < total; idx += stride) {
+    if (!FIXED) { m = idx / CG; c0 = (int)(idx % CG) * VEC; }
     float gv[VEC], yv[VEC];
     if (VEC == 8) {
       ld8<TI>(g + m * C + c0, reinterpret_cast<float(&)[8]>(gv));
@@ -320,16 +374,22 @@ __global__ void __launch_bounds__(256) act_bn_bwd_apply_kernel(
     for (int i = 0; i < VEC; ++i) {
       int c = c0 + i;
       if (mean) {
-        float pre = scale[c] * yv[i] + shift[c];
-        float gp = gv[i] * act_grad(act, slope, pre, 0);
-        float xh = (yv[i] - mean[c]) * invstd[c];
-        gv[i] = gamma[c] * invstd[c] * (gp - (xh * dgamma[c] + dbeta[c]) * inv_m);
+        if (FIXED) {
+          float gp = gv[i] * act_grad(act, slope, sc[i] * yv[i] + sh[i], 0);
+          gv[i] = cA[i] * (gp - ((yv[i] - cM[i]) * cB[i] + cD[i]));
+        } else {
+          float pre = scale[c] * yv[i] + shift[c];
+          float gp = gv[i] * act_grad(act, slope, pre, 0);
+          float xh = (yv[i] - mean[c]) * invstd[c];
+          gv[i] = gamma[c] * invstd[c] * (gp - (xh * dgamma[c] + dbeta[c]) * inv_m);
+        }
       } else {
         gv[i] = gv[i] * act_grad(act, slope, yv[i], use_output);
       }
     }
     if (VEC == 8) st8<TO>(gy + m * C + c0, reinterpret_cast<const float(&)[8]>(gv));
     else st<TO>(gy, m * C + c0, gv[0]);
+    if (FIXED) m += mstep;
   }
 }
 
@@ -507,11 +567,14 @@ int mcg_affine_act_noise(const void* y, long long M, int C, long long P, int dty
   dispatch2(dtype, out_dtype, [&](auto ti, auto to) {
     using TI = decltype(ti);
     using TO = decltype(to);
-    if (C % 8 == 0)
-      affine_act_noise_kernel<TI, TO, 8><<<grid_for(M * (C / 8)), 256, 0, st>>>(
+    if (C % 8 == 0 && 256 % (C / 8) == 0)   // a thread keeps its channel group: per-channel constants in registers
+      affine_act_noise_kernel<TI, TO, 8, true><<<grid_for(M * (C / 8)), 256, 0, st>>>(
+          (const TI*)y, M, C, P, scale, shift, act, slope, sigma, noise, ns_n, ns_c, ns_p, rng, call_id, (TO*)out);
+    else if (C % 8 == 0)
+      affine_act_noise_kernel<TI, TO, 8, false><<<grid_for(M * (C / 8)), 256, 0, st>>>(
           (const TI*)y, M, C, P, scale, shift, act, slope, sigma, noise, ns_n, ns_c, ns_p, rng, call_id, (TO*)out);
     else
-      affine_act_noise_kernel<TI, TO, 1><<<grid_for(M * C), 256, 0, st>>>(
+      affine_act_noise_kernel<TI, TO, 1, false><<<grid_for(M * C), 256, 0, st>>>(
           (const TI*)y, M, C, P, scale, shift, act, slope, sigma, noise, ns_n, ns_c, ns_p, rng, call_id, (TO*)out);
   });
   MCG_CHECK_LAUNCH("mcg_affine_act_noise");
@@ -562,12 +625,16 @@ int mcg_act_bn_bwd_apply(const void* g, const void* y, long long M, int C, int d
   dispatch2(dtype, out_dtype, [&](auto ti, auto to) {
     using TI = decltype(ti);
     using TO = decltype(to);
-    if (C % 8 == 0)
-      act_bn_bwd_apply_kernel<TI, TO, 8><<<grid_for(M * (C / 8)), 256, 0, st>>>(
+    if (C % 8 == 0 && 256 % (C / 8) == 0)
+      act_bn_bwd_apply_kernel<TI, TO, 8, true><<<grid_for(M * (C / 8)), 256, 0, st>>>(
+          (const TI*)g, (const TI*)y, M, C, mean, invstd, gamma, scale, shift, act, slope, use_output, dgamma, dbeta,
+          inv_m, (TO*)gy);
+    else if (C % 8 == 0)
+      act_bn_bwd_apply_kernel<TI, TO, 8, false><<<grid_for(M * (C / 8)), 256, 0, st>>>(
           (const TI*)g, (const TI*)y, M, C, mean, invstd, gamma, scale, shift, act, slope, use_output, dgamma, dbeta,
           inv_m, (TO*)gy);
     else
-      act_bn_bwd_apply_kernel<TI, TO, 1><<<grid_for(M * C), 256, 0, st>>>(
+      act_bn_bwd_apply_kernel<TI, TO, 1, false><<<grid_for(M * C), 256, 0, st>>>(
           (const TI*)g, (const TI*)y, M, C, mean, invstd, gamma, scale, shift, act, slope, use_output, dgamma, dbeta,
           inv_m, (TO*)gy);
   });

@@ -55,7 +55,8 @@ struct TcParams {
 
 __device__ int g_tc_error = 0;
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;      // warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int kEpiThreads = 256;
 constexpr int A_BYTES = 128 * 128;  // 128 rows x 64 bf16
 
 struct TcSeg {
@@ -106,30 +107,15 @@ __device__ __forceinline__ TcBox tc_decode_box(const TcParams& P, int bi) {
   return b;
 }
 
-// column sums over the warp's 32 rows of a 32-column chunk: after the butterfly lane j holds the sum of column j
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < o; ++i) {
-      const float send = up ? v[i] : v[i + o];
-      const float keep = up ? v[i + o] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-  }
-  return v[0];
-}
-
-template <int MODE, int BN, int MT, int STAGES, int OCC>
-__global__ void __launch_bounds__(kTcThreads, OCC) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA,
+template <int MODE, int BN, int MT, int STAGES>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                 const __grid_constant__ CUtensorMap mapB,
                                                                 const __grid_constant__ TcParams P, void* __restrict__ out,
-                                                                const float* __restrict__ bias, float* __restrict__ stats) {
+                                                                const float* __restrict__ bias) {
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
   constexpr int ACC_COLS = MT * BN;                       // fp32 accumulator columns of one tile
-  constexpr int NBUF = (2 * ACC_COLS <= 512 / OCC) ? 2 : 1;   // double-buffered accumulators when they fit in TMEM (512 columns per SM, shared by OCC CTAs)
+  constexpr int NBUF = (2 * ACC_COLS <= 512) ? 2 : 1;     // double-buffered accumulators when they fit in the 512 TMEM columns
   constexpr int TMEM_NEED = NBUF * ACC_COLS;
   constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : (TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512)));
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -141,7 +127,7 @@ __global__ void __launch_bounds__(kTcThreads, OCC) tc_conv_kernel(const __grid_c
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiThreads); }
     fence_barrier_init();
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
@@ -285,7 +271,9 @@ __global__ void __launch_bounds__(kTcThreads, OCC) tc_conv_kernel(const __grid_c
     }
   } else {
     // ================================================= epilogue ============================================
-    const int q = warp & 3;
+    // A lone warp per scheduler runs the epilogue's dependent instruction chains at a fraction of the issue rate, so two
+    // warps share each TMEM lane quarter and take alternate 32-column chunks.
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // accumulator row == TMEM lane
     TcSegIter<MODE, MT> iter(P);
     TcSeg sg;
@@ -316,7 +304,7 @@ __global__ void __launch_bounds__(kTcThreads, OCC) tc_conv_kernel(const __grid_c
           const bool valid = ow < P.full_w && oh < P.full_h && ot < P.full_t && on < P.EN;
           const long long base = (long long)on * P.os_n + (long long)ot * P.os_t + (long long)oh * P.os_h + (long long)ow * P.os_w + ncol0;
 #pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 32) {
+          for (int c0 = half * 32; c0 < BN; c0 += 64) {
             uint32_t v[32];
             if (have_acc) {
               tmem_ld32(acc + m * BN + c0, v);
@@ -362,20 +350,6 @@ __global__ void __launch_bounds__(kTcThreads, OCC) tc_conv_kernel(const __grid_c
                 }
               }
             }
-            if (stats) {
-              // BatchNorm statistics of the values just produced (what the next pass would re-read from HBM): per-column
-              // sum and sum of squares over this warp's 32 rows, one fp32 red.add per column per warp.
-              float sq[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                if (!valid) f[i] = 0.f;
-                else if (!P.out_f32) f[i] = __bfloat162float(__float2bfloat16_rn(f[i]));   // statistics of the stored values
-                sq[i] = f[i] * f[i];
-              }
-              const float s1 = warp_colsum32(f, lane), s2 = warp_colsum32(sq, lane);
-              atomicAdd(stats + ncol0 + c0 + lane, s1);
-              atomicAdd(stats + P.ocols + ncol0 + c0 + lane, s2);
-            }
           }
         }
       } else {
@@ -388,7 +362,7 @@ __global__ void __launch_bounds__(kTcThreads, OCC) tc_conv_kernel(const __grid_c
           const long long kidx = (long long)tp.kidx * P.Cin + (u % P.chunks) * 64 + (r & 63);
           const bool row_ok = live && kidx < P.kreal && have_acc && !P.debug_skip_epi;
 #pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 32) {
+          for (int c0 = half * 32; c0 < BN; c0 += 64) {
             uint32_t v[32];
             if (have_acc) {
               tmem_ld32(acc + m * BN + c0, v);
@@ -503,7 +477,7 @@ static Box choose_box(int target, int W, int H, int T, int B) {
 // into shared memory and issues MT*4 MMAs (2*MT*BN tensor cycles).  The kernel is persistent (one CTA per SM), so the
 // cost of a shape is waves x (K steps x max(tensor cycles, bytes / L2 share)) — wide tiles raise FLOP/byte, small
 // tiles fill the machine when a layer has few pixels.
-struct TileCfg { int mt, bn, occ; };
+struct TileCfg { int mt, bn; };
 static int tc_env_int(const char* name) {
   const char* v = getenv(name);
   return v ? atoi(v) : 0;
@@ -520,7 +494,7 @@ static double step_cycles(int mt, int bn, long long active_ctas) {
 static TileCfg pick_tile(int mode, long long nboxes, int ncls, int cols, int nk) {
   const int fm = tc_env_int("MCG_TC_MT"), fb = tc_env_int("MCG_TC_BN");
   const int sms = num_sms();
-  TileCfg best{1, 64, 1};
+  TileCfg best{1, 64};
   double best_cost = 1e300;
   const int bns[4] = {256, 192, 128, 64};
   for (int bi = 0; bi < 4; ++bi) {
@@ -537,15 +511,14 @@ static TileCfg pick_tile(int mode, long long nboxes, int ncls, int cols, int nk)
       const long long full = upc / mt, rem = upc % mt;
       const double cost = (double)nk * ((double)full * step_cycles(mt, bn, ctas) + (rem ? step_cycles((int)rem, bn, ctas) : 0.0)) +
                           (double)(full + (rem ? 1 : 0)) * 300.0 + mt * bn * 6.0;
-      if (cost < best_cost) { best_cost = cost; best = TileCfg{mt, bn, 1}; }
+      if (cost < best_cost) { best_cost = cost; best = TileCfg{mt, bn}; }
     }
   }
-  if (tc_env_int("MCG_TC_OCC") == 2 && best.mt <= 2 && best.bn != 192 && !(best.mt == 2 && best.bn == 256)) best.occ = 2;
   return best;
 }
 // cut `units` into equal contiguous ranges, one per CTA
-static int split_units(TcParams& P, long long units, long long min_per_cta, int occ = 1) {
-  const int sms = num_sms() * occ;
+static int split_units(TcParams& P, long long units, long long min_per_cta) {
+  const int sms = num_sms();
   long long ctas = units / (min_per_cta > 0 ? min_per_cta : 1);
   if (ctas > sms) ctas = sms;
   if (ctas < 1) ctas = 1;
@@ -554,37 +527,34 @@ static int split_units(TcParams& P, long long units, long long min_per_cta, int 
   return (int)((units + P.units_per_cta - 1) / P.units_per_cta);
 }
 
-template <int MODE, int BN, int MT, int OCC>
+template <int MODE, int BN, int MT>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, int grid, void* out, const float* bias,
-                     float* stats, cudaStream_t st, const char* who) {
+                     cudaStream_t st, const char* who) {
   constexpr int STAGE = MT * A_BYTES + BN * 128;
-  constexpr int BUDGET = (OCC == 2 ? 110 : 220) * 1024;
+  constexpr int BUDGET = 220 * 1024;
   constexpr int STAGES = (BUDGET / STAGE) > 8 ? 8 : (BUDGET / STAGE);
   static_assert(STAGES >= 2, "ring too shallow");
   size_t smem = (size_t)STAGES * STAGE + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<MODE, BN, MT, STAGES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<MODE, BN, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) MCG_FAIL((int)e, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
     configured = true;
   }
-  tc_conv_kernel<MODE, BN, MT, STAGES, OCC><<<grid, kTcThreads, smem, st>>>(ma, mb, P, out, bias, stats);
+  tc_conv_kernel<MODE, BN, MT, STAGES><<<grid, kTcThreads, smem, st>>>(ma, mb, P, out, bias);
   MCG_CHECK_LAUNCH(who);
   return 0;
 }
 template <int MODE>
 static int launch_tc_cfg(TileCfg c, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, int grid, void* out,
-                         const float* bias, float* stats, cudaStream_t st, const char* who) {
-#define MCG_TC_CASE(bn_, mt_, occ_) \
-  if (c.bn == bn_ && c.mt == mt_ && c.occ == occ_) return launch_tc<MODE, bn_, mt_, occ_>(ma, mb, P, grid, out, bias, stats, st, who)
-  MCG_TC_CASE(64, 1, 1); MCG_TC_CASE(64, 2, 1);
-  MCG_TC_CASE(64, 1, 2); MCG_TC_CASE(64, 2, 2);
-  if (MODE != kWgrad) { MCG_TC_CASE(64, 4, 1); }
-  MCG_TC_CASE(128, 1, 1); MCG_TC_CASE(128, 2, 1);
-  MCG_TC_CASE(128, 1, 2); MCG_TC_CASE(128, 2, 2);
-  MCG_TC_CASE(256, 1, 1); MCG_TC_CASE(256, 2, 1);
-  MCG_TC_CASE(256, 1, 2);
-  if (MODE == kFprop) { MCG_TC_CASE(192, 1, 1); MCG_TC_CASE(192, 2, 1); }
+                         const float* bias, cudaStream_t st, const char* who) {
+#define MCG_TC_CASE(bn_, mt_) \
+  if (c.bn == bn_ && c.mt == mt_) return launch_tc<MODE, bn_, mt_>(ma, mb, P, grid, out, bias, st, who)
+  MCG_TC_CASE(64, 1); MCG_TC_CASE(64, 2);
+  if (MODE != kWgrad) { MCG_TC_CASE(64, 4); }
+  MCG_TC_CASE(128, 1); MCG_TC_CASE(128, 2);
+  MCG_TC_CASE(256, 1); MCG_TC_CASE(256, 2);
+  if (MODE == kFprop) { MCG_TC_CASE(192, 1); MCG_TC_CASE(192, 2); }
 #undef MCG_TC_CASE
   MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: tile %dx%d", who, c.mt * 128, c.bn);
 }
@@ -597,9 +567,8 @@ bool tc_supported(const mcg_conv_geom* g) {
   return true;
 }
 
-// stats: optional [2][ocols] fp32 accumulator (zeroed by the caller) that receives per-output-channel sum / sum of squares
 int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void* out, const float* bias, int out_dtype,
-            cudaStream_t st, int kreal = 0, int planar_chunk = 0, int planar_cols = 0, float* stats = nullptr) {
+            cudaStream_t st, int kreal = 0, int planar_chunk = 0, int planar_cols = 0) {
   const char* who = mode == kFprop ? "mcg_conv_fprop(tc)" : mode == kDgrad ? "mcg_conv_dgrad(tc)" : "mcg_conv_wgrad(tc)";
   if (!tc_supported(g)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: needs Cin,Cout %% 64 == 0, stride <= 2, <= 64 taps", who);
   TcParams P;
@@ -634,11 +603,11 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
     const TileCfg cfg = pick_tile(kFprop, P.nboxes, 1, g->Cout, taps * P.chunks);
     P.ntn = g->Cout / cfg.bn;
     P.ntiles = P.ntn;
-    const int grid = split_units(P, (long long)P.ntiles * P.nboxes, 1, cfg.occ);
+    const int grid = split_units(P, (long long)P.ntiles * P.nboxes, 1);
     uint64_t d2[2] = {(uint64_t)P.Ktot, (uint64_t)g->Cout}, s2[1] = {(uint64_t)P.Ktot * 2};
     uint32_t b2[2] = {64, (uint32_t)cfg.bn}, e2[2] = {1, 1};
     if ((rc = get_map(&mb, b, 2, d2, s2, b2, e2))) return rc;
-    return launch_tc_cfg<kFprop>(cfg, ma, mb, P, grid, out, bias, stats, st, who);
+    return launch_tc_cfg<kFprop>(cfg, ma, mb, P, grid, out, bias, st, who);
   }
   if (mode == kDgrad) {
     // a = dy (N,To,Ho,Wo,Cout), b = w bf16, out = dx (N,Ti,Hi,Wi,Cin); one class per residue of the input coordinate
@@ -680,11 +649,11 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
     const TileCfg cfg = pick_tile(kDgrad, P.nboxes, ncls, g->Cin, max_taps * P.chunks);
     P.ntn = g->Cin / cfg.bn;
     P.ntiles = ncls * P.ntn;
-    const int grid = split_units(P, (long long)P.ntiles * P.nboxes, 1, cfg.occ);
+    const int grid = split_units(P, (long long)P.ntiles * P.nboxes, 1);
     uint64_t d2[2] = {(uint64_t)P.Ktot, (uint64_t)g->Cout}, s2[1] = {(uint64_t)P.Ktot * 2};
     uint32_t b2[2] = {64, 64}, e2[2] = {1, 1};
     if ((rc = get_map(&mb, b, 2, d2, s2, b2, e2))) return rc;
-    return launch_tc_cfg<kDgrad>(cfg, ma, mb, P, grid, out, bias, stats, st, who);
+    return launch_tc_cfg<kDgrad>(cfg, ma, mb, P, grid, out, bias, st, who);
   }
   // ---- wgrad: a = x (N,Ti,Hi,Wi,Cin), b = dy (N,To,Ho,Wo,Cout), out = dw fp32 (Cout, taps*Cin), accumulated
   {
@@ -703,7 +672,7 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
     P.total_boxes = P.nbw * P.nbh * P.nbt * P.nbb;
     // widest tile the channel counts allow: B (dy) is re-read once per row group, A (x) once per column tile, and the
     // fp32 red.add volume grows with the number of K splits, so few large tiles win; stream-K keeps every SM busy.
-    TileCfg cfg{slabs >= 4 ? 2 : 1, 64, 1};
+    TileCfg cfg{slabs >= 4 ? 2 : 1, 64};
     for (int c = 256; c >= 64; c /= 2)
       if (g->Cout % c == 0) { cfg.bn = c; break; }
     if (tc_env_int("MCG_TC_WMT")) cfg.mt = tc_env_int("MCG_TC_WMT");
@@ -711,11 +680,10 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
     const int mgroups = ceil_div(slabs, 2 * cfg.mt);
     P.ntn = g->Cout / cfg.bn;
     P.ntiles = mgroups * P.ntn;
-    if (tc_env_int("MCG_TC_OCC") == 2 && !(cfg.bn == 256 && cfg.mt == 2)) cfg.occ = 2;
-    const int ctas = split_units(P, (long long)P.ntiles * P.total_boxes, 8, cfg.occ);   // at least 8 K steps per CTA
+    const int ctas = split_units(P, (long long)P.ntiles * P.total_boxes, 8);   // at least 8 K steps per CTA
     if ((rc = act_map(&ma, a, g->Cin, g->Wi, g->Hi, g->Ti, g->N, bx.w, bx.h, bx.t, bx.b, g->sW, g->sH, g->sT))) return rc;
     if ((rc = act_map(&mb, b, g->Cout, g->Wo, g->Ho, g->To, g->N, bx.w, bx.h, bx.t, bx.b, 1, 1, 1))) return rc;
-    return launch_tc_cfg<kWgrad>(cfg, ma, mb, P, ctas, out, nullptr, nullptr, st, who);
+    return launch_tc_cfg<kWgrad>(cfg, ma, mb, P, ctas, out, nullptr, st, who);
   }
 }
 
@@ -765,23 +733,27 @@ template <int CIN, int KW>
 __global__ void __launch_bounds__(128) im2col_line_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ cols,
                                                           int Kp, int Ti, int Hi, int Wi, int To, int Ho, int Wo, int kT, int kH,
                                                           int sT, int sH, int sW, int pT, int pH, int pW) {
-  extern __shared__ unsigned short rows[];  // [kT*kH][L]
+  extern __shared__ __align__(16) unsigned short rows[];  // [kT*kH][L]: 8 zeros | Wi*CIN source values | 8 zeros
   const int runs = kT * kH;
-  const int L = (Wi + pW + KW) * CIN;
+  const int RW = Wi * CIN;                  // launcher guarantees RW % 8 == 0, pW*CIN <= 8, (KW-pW-1)*CIN <= 8
+  const int L = RW + 16;
   const int K = runs * KW * CIN;
   int line = blockIdx.x;
   const int ho = line % Ho; line /= Ho;
   const int to = line % To;
   const long long n = line / To;
-  const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
-  for (int run = 0; run < runs; ++run) {
-    const int kh = run % kH, kt = run / kH;
-    const int ti = to * sT - pT + kt, hi = ho * sH - pH + kh;
-    const bool row_ok = (unsigned)ti < (unsigned)Ti && (unsigned)hi < (unsigned)Hi;
-    const long long src = (((n * Ti + ti) * Hi + hi) * (long long)Wi) * CIN;
-    for (int e = threadIdx.x; e < L; e += blockDim.x) {
-      const int w = e / CIN - pW;
-      rows[run * L + e] = (row_ok && (unsigned)w < (unsigned)Wi) ? __ldg(xs + src + (e - pW * CIN)) : (unsigned short)0;
+  {
+    // source rows are copied with 16-byte loads (a row of the channels-last clip is contiguous and 16-byte aligned)
+    const int vpr_src = RW / 8 + 2;         // vectors per staged row, pads included
+    uint4* rows128 = reinterpret_cast<uint4*>(rows);
+    for (int e = threadIdx.x; e < runs * vpr_src; e += blockDim.x) {
+      const int run = e / vpr_src, j = e - run * vpr_src;
+      const int kh = run % kH, kt = run / kH;
+      const int ti = to * sT - pT + kt, hi = ho * sH - pH + kh;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (j > 0 && j <= RW / 8 && (unsigned)ti < (unsigned)Ti && (unsigned)hi < (unsigned)Hi)
+        v = __ldg(reinterpret_cast<const uint4*>(x + (((n * Ti + ti) * Hi + hi) * (long long)Wi) * CIN) + (j - 1));
+      rows128[e] = v;
     }
   }
   __syncthreads();
@@ -795,7 +767,7 @@ __global__ void __launch_bounds__(128) im2col_line_kernel(const __nv_bfloat16* _
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int k = kv * 8 + i;
-    off[i] = k < K ? (k / (KW * CIN)) * L + k % (KW * CIN) : -1;
+    off[i] = k < K ? (k / (KW * CIN)) * L + (8 - pW * CIN) + k % (KW * CIN) : -1;
   }
   const long long m0 = ((n * To + to) * Ho + ho) * (long long)Wo;
   uint4* dst = reinterpret_cast<uint4*>(cols + m0 * Kp);
@@ -945,11 +917,13 @@ int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b
   const void* x = a;
   if (!cols_valid) {
     const long long lines = (long long)g->N * g->To * g->Ho;
-    const size_t smem = (size_t)g->kT * g->kH * (g->Wi + g->pW + g->kW) * g->Cin * 2;
-    if (g->kW == 4 && g->Cin == 3 && lines < 0x7fffffffLL && smem <= 48 * 1024)
+    const size_t smem = (size_t)g->kT * g->kH * (g->Wi * g->Cin + 16) * 2;
+    const bool line_ok = lines < 0x7fffffffLL && smem <= 48 * 1024 && (g->Wi * g->Cin) % 8 == 0 && g->pW * g->Cin <= 8 &&
+                         (g->kW - g->pW - 1) * g->Cin <= 8 && (g->Wo - 1) * g->sW - g->pW + g->kW - 1 <= g->Wi + (8 / g->Cin) - 1;
+    if (g->kW == 4 && g->Cin == 3 && line_ok)
       im2col_line_kernel<3, 4><<<(unsigned)lines, 128, smem, st>>>((const __nv_bfloat16*)x, cols, Kp, g->Ti, g->Hi, g->Wi, g->To, g->Ho,
                                                                    g->Wo, g->kT, g->kH, g->sT, g->sH, g->sW, g->pT, g->pH, g->pW);
-    else if (g->kW == 4 && g->Cin == 1 && lines < 0x7fffffffLL && smem <= 48 * 1024)
+    else if (g->kW == 4 && g->Cin == 1 && line_ok)
       im2col_line_kernel<1, 4><<<(unsigned)lines, 128, smem, st>>>((const __nv_bfloat16*)x, cols, Kp, g->Ti, g->Hi, g->Wi, g->To, g->Ho,
                                                                    g->Wo, g->kT, g->kH, g->sT, g->sH, g->sW, g->pT, g->pH, g->pW);
     else
