@@ -74,6 +74,11 @@ __global__ void __launch_bounds__(kGruWarps * 32) gru_forward_kernel(GruPtrs P, 
   }
 }
 
+// Backward through the T steps.  Lane j owns row j of every weight matrix; its parameter gradients are accumulated in
+// REGISTERS over all T steps (H <= kGruMaxH) and reach global memory with one red.add per element at the end — the
+// per-step shared-memory float atomics of the first version (a CAS loop each, four warps on the same addresses) were
+// 90 % of this kernel's time.
+constexpr int kGruMaxH = 16;
 __global__ void __launch_bounds__(kGruWarps * 32) gru_backward_kernel(GruPtrs P, GruGrads G, const int* __restrict__ labels,
                                                                       int L, const float* __restrict__ eps,
                                                                       const float* __restrict__ cache,
@@ -83,75 +88,68 @@ __global__ void __launch_bounds__(kGruWarps * 32) gru_backward_kernel(GruPtrs P,
   float* W[12];
   const int I = L + H;
   gru_load_weights(P, H, I, sm, W);
-  const int total = 3 * (H * I + H * H) + 6 * H;
-  float* gs = sm + total;  // gradient accumulators, same layout
-  for (int i = threadIdx.x; i < total; i += blockDim.x) gs[i] = 0.f;
-  float* GW[12];
-  {
-    int sizes[12] = {H * I, H, H * H, H, H * I, H, H * H, H, H * I, H, H * H, H};
-    int off = 0;
-    for (int a = 0; a < 12; ++a) { GW[a] = gs + off; off += sizes[a]; }
-  }
   __syncthreads();
   const int warp = threadIdx.x / 32, j = threadIdx.x % 32;
   const int n = blockIdx.x * kGruWarps + warp;
-  if (n < N) {
-    const bool on = j < H;
-    const int jj = on ? j : 0;
-    const int label = (labels && L > 0) ? labels[n] : -1;
-    const int ZW = Zc + H;
-    float gh = 0.f;
-    for (int t = T - 1; t >= 0; --t) {
-      long long row = (long long)t * N + n;
-      const float* c = cache + (row * 4) * H;
-      float r = on ? c[j] : 0.f, z = on ? c[H + j] : 0.f, hb = on ? c[2 * H + j] : 0.f, hp = on ? c[3 * H + j] : 0.f;
-      float e = on ? eps[row * H + j] : 0.f;
-      if (on) gh += gz[row * ZW + Zc + j];
-      float gzg = gh * (hb - hp), ghb = gh * z, ghp = gh * (1.f - z);
-      float ga = ghb * (1.f - hb * hb);
-      float grh = 0.f;
-      for (int q = 0; q < H; ++q) grh += __shfl_sync(0xffffffffu, ga, q) * W[10][q * H + jj];
-      float gr = grh * hp;
-      ghp += grh * r;
-      float gzp = gzg * z * (1.f - z), grp = gr * r * (1.f - r);
-      float back = 0.f;
-      for (int q = 0; q < H; ++q)
-        back += __shfl_sync(0xffffffffu, gzp, q) * W[6][q * H + jj] + __shfl_sync(0xffffffffu, grp, q) * W[2][q * H + jj];
-      ghp += back;
-      float rh = r * hp;
-      // parameter gradients: lane j owns row j of every matrix
-      for (int k = 0; k < H; ++k) {
+  if (n >= N) return;
+  const bool on = j < H;
+  const int jj = on ? j : 0;
+  const int label = (labels && L > 0) ? labels[n] : -1;
+  const int ZW = Zc + H;
+  float aWr[kGruMaxH], aWz[kGruMaxH], aW[kGruMaxH], aUr[kGruMaxH], aUz[kGruMaxH], aU[kGruMaxH];
+#pragma unroll
+  for (int k = 0; k < kGruMaxH; ++k) aWr[k] = aWz[k] = aW[k] = aUr[k] = aUz[k] = aU[k] = 0.f;
+  float sr = 0.f, sz = 0.f, sa = 0.f;   // sums over t of grp, gzp, ga: the bias and label-column gradients
+  float gh = 0.f;
+  for (int t = T - 1; t >= 0; --t) {
+    long long row = (long long)t * N + n;
+    const float* c = cache + (row * 4) * H;
+    float r = on ? c[j] : 0.f, z = on ? c[H + j] : 0.f, hb = on ? c[2 * H + j] : 0.f, hp = on ? c[3 * H + j] : 0.f;
+    float e = on ? eps[row * H + j] : 0.f;
+    if (on) gh += gz[row * ZW + Zc + j];
+    float gzg = gh * (hb - hp), ghb = gh * z, ghp = gh * (1.f - z);
+    float ga = ghb * (1.f - hb * hb);
+    float grh = 0.f;
+    for (int q = 0; q < H; ++q) grh += __shfl_sync(0xffffffffu, ga, q) * W[10][q * H + jj];
+    float gr = grh * hp;
+    ghp += grh * r;
+    float gzp = gzg * z * (1.f - z), grp = gr * r * (1.f - r);
+    float back = 0.f;
+    for (int q = 0; q < H; ++q)
+      back += __shfl_sync(0xffffffffu, gzp, q) * W[6][q * H + jj] + __shfl_sync(0xffffffffu, grp, q) * W[2][q * H + jj];
+    ghp += back;
+    float rh = r * hp;
+#pragma unroll
+    for (int k = 0; k < kGruMaxH; ++k) {
+      if (k < H) {   // warp-uniform
         float ek = __shfl_sync(0xffffffffu, e, k), hk = __shfl_sync(0xffffffffu, hp, k), rhk = __shfl_sync(0xffffffffu, rh, k);
-        if (on) {
-          atomicAdd(&GW[0][j * I + L + k], grp * ek);
-          atomicAdd(&GW[4][j * I + L + k], gzp * ek);
-          atomicAdd(&GW[8][j * I + L + k], ga * ek);
-          atomicAdd(&GW[2][j * H + k], grp * hk);
-          atomicAdd(&GW[6][j * H + k], gzp * hk);
-          atomicAdd(&GW[10][j * H + k], ga * rhk);
-        }
+        aWr[k] = fmaf(grp, ek, aWr[k]); aWz[k] = fmaf(gzp, ek, aWz[k]); aW[k] = fmaf(ga, ek, aW[k]);
+        aUr[k] = fmaf(grp, hk, aUr[k]); aUz[k] = fmaf(gzp, hk, aUz[k]); aU[k] = fmaf(ga, rhk, aU[k]);
       }
-      if (on) {
-        if (label >= 0) {
-          atomicAdd(&GW[0][j * I + label], grp);
-          atomicAdd(&GW[4][j * I + label], gzp);
-          atomicAdd(&GW[8][j * I + label], ga);
-        }
-        atomicAdd(&GW[1][j], grp); atomicAdd(&GW[3][j], grp);
-        atomicAdd(&GW[5][j], gzp); atomicAdd(&GW[7][j], gzp);
-        atomicAdd(&GW[9][j], ga);  atomicAdd(&GW[11][j], ga);
-      }
-      gh = ghp;
     }
+    sr += grp; sz += gzp; sa += ga;
+    gh = ghp;
   }
-  __syncthreads();
-  {
-    int sizes[12] = {H * I, H, H * H, H, H * I, H, H * H, H, H * I, H, H * H, H};
-    int off = 0;
-    for (int a = 0; a < 12; ++a) {
-      for (int i = threadIdx.x; i < sizes[a]; i += blockDim.x) atomicAdd(&G.p[a][i], gs[off + i]);
-      off += sizes[a];
+  if (on) {
+#pragma unroll
+    for (int k = 0; k < kGruMaxH; ++k) {
+      if (k < H) {
+        atomicAdd(&G.p[0][j * I + L + k], aWr[k]);
+        atomicAdd(&G.p[4][j * I + L + k], aWz[k]);
+        atomicAdd(&G.p[8][j * I + L + k], aW[k]);
+        atomicAdd(&G.p[2][j * H + k], aUr[k]);
+        atomicAdd(&G.p[6][j * H + k], aUz[k]);
+        atomicAdd(&G.p[10][j * H + k], aU[k]);
+      }
     }
+    if (label >= 0) {
+      atomicAdd(&G.p[0][j * I + label], sr);
+      atomicAdd(&G.p[4][j * I + label], sz);
+      atomicAdd(&G.p[8][j * I + label], sa);
+    }
+    atomicAdd(&G.p[1][j], sr); atomicAdd(&G.p[3][j], sr);
+    atomicAdd(&G.p[5][j], sz); atomicAdd(&G.p[7][j], sz);
+    atomicAdd(&G.p[9][j], sa); atomicAdd(&G.p[11][j], sa);
   }
 }
 
@@ -260,7 +258,8 @@ int mcg_gru_backward(const float* const* params_host, float* const* grads_host, 
   GruPtrs P;
   GruGrads G;
   for (int i = 0; i < 12; ++i) { P.p[i] = params_host[i]; G.p[i] = grads_host[i]; }
-  size_t smem = (size_t)(3 * (H * (L + H) + H * H) + 6 * H) * sizeof(float) * 2;
+  if (H > kGruMaxH) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_gru_backward: H = %d > %d", H, kGruMaxH);
+  size_t smem = (size_t)(3 * (H * (L + H) + H * H) + 6 * H) * sizeof(float);
   gru_backward_kernel<<<(N + kGruWarps - 1) / kGruWarps, kGruWarps * 32, smem, as_stream(stream)>>>(
       P, G, labels, L, eps, cache, gz, T, N, H, Zc);
   MCG_CHECK_LAUNCH("mcg_gru_backward");

@@ -50,6 +50,7 @@ struct TcParams {
   int out_f32, ocols;                                        // ocols = channels of one output pixel row
   int planar_chunk, planar_cols;   // fprop: write column c to plane c/chunk as [plane][pixel][chunk] (0 = row-major)
   long long planar_stride;
+  uint8_t planar_plane[64], planar_within[64];   // per 4-column group c/4: plane index and offset inside the plane's chunk
   TcTap taps[64];
 };
 
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                 for (int i = 0; i < 32; i += 4) {
                   const int c = ncol0 + c0 + i;
                   if (c < P.planar_cols) {
-                    const int plane = c / P.planar_chunk, within = c - plane * P.planar_chunk;
+                    const int plane = P.planar_plane[c >> 2], within = P.planar_within[c >> 2];
                     uint2 u;
                     __nv_bfloat162 lo = __floats2bfloat162_rn(f[i], f[i + 1]), hi = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
                     u.x = *reinterpret_cast<uint32_t*>(&lo);
@@ -579,6 +580,13 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
   P.planar_chunk = planar_chunk;
   P.planar_cols = planar_cols;
   P.planar_stride = (long long)g->Wo * planar_chunk;   // planar mode is only used on 1-D line geometries (M = Wo)
+  if (planar_chunk) {
+    if (planar_chunk % 4 || planar_cols > 256) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: planar chunk %d / cols %d", who, planar_chunk, planar_cols);
+    for (int c = 0; c < planar_cols; c += 4) {
+      P.planar_plane[c >> 2] = (uint8_t)(c / planar_chunk);
+      P.planar_within[c >> 2] = (uint8_t)(c % planar_chunk);
+    }
+  }
   CUtensorMap ma, mb;
   int rc;
   if (mode == kFprop) {
@@ -806,48 +814,29 @@ __global__ void __launch_bounds__(128) col2im_line_kernel(const __nv_bfloat16* _
                                                           void* __restrict__ dx, int out_f32, long long Mpix, int Cin, int Ti, int Hi,
                                                           int Wi, int To, int Ho, int Wo, int kT, int kH, int kW, int sT, int sH,
                                                           int sW, int pT, int pH, int pW) {
-  extern __shared__ __align__(16) unsigned short zs[];  // [valid runs][Wo][kW*Cin]
-  __shared__ int run_row[64], run_col[64];
-  __shared__ int nvalid;
+  // slot (kt, kh) of the staging buffer holds the Wo*kW*Cin values of that (kt,kh) run if it reaches this input line,
+  // zeros otherwise: every thread decides that for the vectors it copies, so there is no serial set-up phase
+  extern __shared__ __align__(16) unsigned short zs[];  // [kT*kH][Wo][kW*Cin]
   const int RUN = kW * Cin;
+  const int slots = kT * kH;
   int line = blockIdx.x;
   const int hi = line % Hi; line /= Hi;
   const int ti = line % Ti;
   const long long n = line / Ti;
-  if (threadIdx.x == 0) {
-    int v = 0;
-    for (int kt = 0; kt < kT; ++kt) {
-      const int tt = ti + pT - kt;
-      if (tt < 0 || tt % sT || tt / sT >= To) continue;
-      for (int kh = 0; kh < kH; ++kh) {
-        const int hh = hi + pH - kh;
-        if (hh < 0 || hh % sH || hh / sH >= Ho) continue;
-        run_row[v] = (int)(((n * To + tt / sT) * Ho + hh / sH));   // Z row block (times Wo)
-        run_col[v] = kt * kH + kh;                                  // plane index
-        ++v;
-      }
-    }
-    nvalid = v;
-  }
-  __syncthreads();
-  const int nv = nvalid;
-  // Z is planar: Z[run][pixel][RUN]; a line needs, per valid run, Wo*RUN contiguous elements
-  if ((Wo * RUN) % 8 == 0) {   // 16-byte copies, all runs of the line in flight together
+  const int vecs = Wo * RUN / 8;   // launcher guarantees (Wo * RUN) % 8 == 0
+  {
     const uint4* zsrc = reinterpret_cast<const uint4*>(Z);
     uint4* zs128 = reinterpret_cast<uint4*>(zs);
-    const int vecs = Wo * RUN / 8;
-    for (int e = threadIdx.x; e < nv * vecs; e += blockDim.x) {
-      const int v = e / vecs, i = e - v * vecs;
-      const long long base = ((long long)run_col[v] * Mpix + (long long)run_row[v] * Wo) * RUN / 8;
-      zs128[e] = __ldg(zsrc + base + i);
-    }
-  } else {
-    const uint32_t* zsrc = reinterpret_cast<const uint32_t*>(Z);
-    uint32_t* zs32 = reinterpret_cast<uint32_t*>(zs);
-    const int words = Wo * RUN / 2;
-    for (int v = 0; v < nv; ++v) {
-      const long long base = ((long long)run_col[v] * Mpix + (long long)run_row[v] * Wo) * RUN / 2;
-      for (int e = threadIdx.x; e < words; e += blockDim.x) zs32[v * words + e] = __ldg(zsrc + base + e);
+    for (int e = threadIdx.x; e < slots * vecs; e += blockDim.x) {
+      const int sl = e / vecs, i = e - sl * vecs;
+      const int kt = sl / kH, kh = sl - kt * kH;
+      const int tt = ti + pT - kt, hh = hi + pH - kh;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (tt >= 0 && hh >= 0 && tt % sT == 0 && hh % sH == 0 && tt / sT < To && hh / sH < Ho) {
+        const long long row = (n * To + tt / sT) * Ho + hh / sH;   // Z row block (times Wo)
+        v = __ldg(zsrc + ((long long)sl * Mpix + row * Wo) * RUN / 8 + i);
+      }
+      zs128[e] = v;
     }
   }
   __syncthreads();
@@ -860,7 +849,7 @@ __global__ void __launch_bounds__(128) col2im_line_kernel(const __nv_bfloat16* _
       if (ww < 0 || ww % sW) continue;
       const int wo = ww / sW;
       if (wo >= Wo) continue;
-      for (int v = 0; v < nv; ++v) {
+      for (int v = 0; v < slots; ++v) {
         const __nv_bfloat16_raw raw = {zs[(v * Wo + wo) * RUN + kw * Cin + ci]};
         acc += __bfloat162float(__nv_bfloat16(raw));
       }
@@ -904,9 +893,8 @@ int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b
     const int RUN = g->kW * g->Cin;
     if ((rc = tc_conv(kFprop, &g2, a, wpad, cols, nullptr, MCG_BF16, st, 0, RUN, K))) return rc;
     const long long lines = (long long)g->N * g->Ti * g->Hi;
-    const int runs_max = ceil_div(g->kT, g->sT) * ceil_div(g->kH, g->sH);
-    const size_t smem = (size_t)runs_max * g->Wo * g->kW * g->Cin * 2;
-    if (lines > 0x7fffffffLL || smem > 48 * 1024 || g->kT * g->kH > 64) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: line too large", who);
+    const size_t smem = (size_t)g->kT * g->kH * g->Wo * g->kW * g->Cin * 2;
+    if (lines > 0x7fffffffLL || smem > 48 * 1024 || (g->Wo * g->kW * g->Cin) % 8) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: line too large", who);
     col2im_line_kernel<<<(unsigned)lines, 128, smem, st>>>(cols, bias, out, out_dtype == MCG_F32, M, g->Cin, g->Ti, g->Hi, g->Wi,
                                                            g->To, g->Ho, g->Wo, g->kT, g->kH, g->kW, g->sT, g->sH, g->sW, g->pT,
                                                            g->pH, g->pW);
