@@ -814,27 +814,30 @@ __global__ void __launch_bounds__(128) col2im_line_kernel(const __nv_bfloat16* _
                                                           void* __restrict__ dx, int out_f32, long long Mpix, int Cin, int Ti, int Hi,
                                                           int Wi, int To, int Ho, int Wo, int kT, int kH, int kW, int sT, int sH,
                                                           int sW, int pT, int pH, int pW) {
-  // slot (kt, kh) of the staging buffer holds the Wo*kW*Cin values of that (kt,kh) run if it reaches this input line,
-  // zeros otherwise: every thread decides that for the vectors it copies, so there is no serial set-up phase
-  extern __shared__ __align__(16) unsigned short zs[];  // [kT*kH][Wo][kW*Cin]
+  // Only the taps whose parity matches this input line can reach it: kt = (ti+pT) % sT + a*sT, kh = (hi+pH) % sH + b*sH.
+  // Slot (a, b) of the staging buffer holds that run's Wo*kW*Cin values (zeros when the run falls outside the output);
+  // every thread decides that for the vectors it copies, so there is no serial set-up phase.
+  extern __shared__ __align__(16) unsigned short zs[];  // [slots][Wo][kW*Cin]
   const int RUN = kW * Cin;
-  const int slots = kT * kH;
+  const int nsh = (kH + sH - 1) / sH, nst = (kT + sT - 1) / sT;
+  const int slots = nst * nsh;
   int line = blockIdx.x;
   const int hi = line % Hi; line /= Hi;
   const int ti = line % Ti;
   const long long n = line / Ti;
+  const int ktp = (ti + pT) % sT, khp = (hi + pH) % sH;
   const int vecs = Wo * RUN / 8;   // launcher guarantees (Wo * RUN) % 8 == 0
   {
     const uint4* zsrc = reinterpret_cast<const uint4*>(Z);
     uint4* zs128 = reinterpret_cast<uint4*>(zs);
     for (int e = threadIdx.x; e < slots * vecs; e += blockDim.x) {
       const int sl = e / vecs, i = e - sl * vecs;
-      const int kt = sl / kH, kh = sl - kt * kH;
-      const int tt = ti + pT - kt, hh = hi + pH - kh;
+      const int kt = ktp + (sl / nsh) * sT, kh = khp + (sl % nsh) * sH;
+      const int tt = (ti + pT - kt) / sT, hh = (hi + pH - kh) / sH;   // exact when the numerators are >= 0
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (tt >= 0 && hh >= 0 && tt % sT == 0 && hh % sH == 0 && tt / sT < To && hh / sH < Ho) {
-        const long long row = (n * To + tt / sT) * Ho + hh / sH;   // Z row block (times Wo)
-        v = __ldg(zsrc + ((long long)sl * Mpix + row * Wo) * RUN / 8 + i);
+      if (kt < kT && kh < kH && ti + pT - kt >= 0 && hi + pH - kh >= 0 && tt < To && hh < Ho) {
+        const long long row = (n * To + tt) * Ho + hh;   // Z row block (times Wo)
+        v = __ldg(zsrc + ((long long)(kt * kH + kh) * Mpix + row * Wo) * RUN / 8 + i);
       }
       zs128[e] = v;
     }
@@ -893,7 +896,7 @@ int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b
     const int RUN = g->kW * g->Cin;
     if ((rc = tc_conv(kFprop, &g2, a, wpad, cols, nullptr, MCG_BF16, st, 0, RUN, K))) return rc;
     const long long lines = (long long)g->N * g->Ti * g->Hi;
-    const size_t smem = (size_t)g->kT * g->kH * g->Wo * g->kW * g->Cin * 2;
+    const size_t smem = (size_t)ceil_div(g->kT, g->sT) * ceil_div(g->kH, g->sH) * g->Wo * g->kW * g->Cin * 2;
     if (lines > 0x7fffffffLL || smem > 48 * 1024 || (g->Wo * g->kW * g->Cin) % 8) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: line too large", who);
     col2im_line_kernel<<<(unsigned)lines, 128, smem, st>>>(cols, bias, out, out_dtype == MCG_F32, M, g->Cin, g->Ti, g->Hi, g->Wi,
                                                            g->To, g->Ho, g->Wo, g->kT, g->kH, g->kW, g->sT, g->sH, g->sW, g->pT,
