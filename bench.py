@@ -151,6 +151,15 @@ def build_updater(batch, seed, use_graph, model="normal"):
     return up, it
 
 
+def load_traffic():
+    """Measured DRAM bytes per launch (ncu --set full) of the kernels profiled under profiles/, keyed kernel:layer."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
 def time_conv_layers(K, torch, peaks):
     """Per-kernel roofline: each tcgen05 convolution launch of the step timed ALONE with CUDA events (burst peak)."""
     layers = [  # name, N, Cin, Cout, in_sp, k, s, p, calls per step as (fprop, dgrad, wgrad) of the conv geometry
@@ -284,7 +293,10 @@ def run_ours(args):
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": {"bound": "tensor", "kernel": dominant["kernel"], "layer": dominant["layer"],
                      "achieved": dominant["tflops"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                     "frac": dominant["frac_of_burst_peak"], "traffic": None, "peak_source": peaks["src"] + " (burst: kernel timed alone)",
+                     "frac": dominant["frac_of_burst_peak"],
+                     "traffic": load_traffic().get("%s:%s" % (dominant["kernel"], dominant["layer"])),
+                     "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "algorithmic_flop_per_launch": dominant["gflop"] * 1e9, "peak_source": peaks["src"] + " (burst: kernel timed alone)",
                      "step": {"useful_gflop": USEFUL_GF_PER_STEP, "achieved_tflops": USEFUL_GF_PER_STEP * steps_per_s / world / 1e3,
                               "peak_sustained": peaks["bf16_sustained"],
                               "frac": USEFUL_GF_PER_STEP * steps_per_s / world / 1e3 / peaks["bf16_sustained"],
