@@ -69,6 +69,7 @@ CONV_CASES = [
     ("dv_dc2", 3, 2, 64, 64, (7, 16, 16), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
     ("dv_dc5", 3, 3, 64, 1, (4, 4, 4), (4, 4, 4), (1, 3, 3), (0, 0, 0)),
     ("g_dc1", 2, 6, 16, 60, (4, 4), (4, 4), (1, 1), (0, 0)),  # deconv 1x1->4x4 seen as its conv
+    ("g_dc1_rows", 2, 300, 32, 60, (4, 4), (4, 4), (1, 1), (0, 0)),  # many rows: the 8-row full-window kernels
     ("odd", 2, 2, 5, 9, (9, 7), (3, 3), (2, 1), (1, 0)),
 ]
 
@@ -111,8 +112,8 @@ def test_conv_simt_fp32(K, case):
     run_conv_case(K, case, K.IMPL_SIMT, torch.float32, TOL_F32)
 
 
-@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[0] in ("di_dc1", "dv_dc1", "g_dc1")],
-                         ids=["di_dc1", "dv_dc1", "g_dc1"])
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[0] in ("di_dc1", "dv_dc1", "g_dc1", "g_dc1_rows")],
+                         ids=["di_dc1", "dv_dc1", "g_dc1", "g_dc1_rows"])
 def test_conv_simt_bf16_activations(K, case):
     run_conv_case(K, case, K.IMPL_SIMT, torch.bfloat16, TOL_BF16)
 
@@ -134,6 +135,24 @@ TC_CASES = [
 @pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
 def test_conv_tcgen05_bf16(K, case):
     run_conv_case(K, case, K.IMPL_TC, torch.bfloat16, TOL_BF16)
+
+
+TILE_SHAPES = [(1, 64), (2, 64), (4, 64), (1, 128), (2, 128), (1, 256), (2, 256)]
+
+
+@pytest.mark.parametrize("mt,bn", TILE_SHAPES, ids=["%dx%d" % (m * 128, b) for m, b in TILE_SHAPES])
+def test_conv_tcgen05_every_tile_shape(K, mt, bn, monkeypatch):
+    """The persistent kernel picks its tile (MT x 128 rows, BN columns) from a cost model; here every shape is forced
+    (MCG_TC_MT / MCG_TC_BN / MCG_TC_WMT / MCG_TC_WBN are read per call) on layers whose box counts leave remainders:
+    partial last steps (nlive < MT), rows cut between CTAs, stream-K cuts inside a wgrad tile, dummy wgrad slabs."""
+    monkeypatch.setenv("MCG_TC_MT", str(mt))
+    monkeypatch.setenv("MCG_TC_BN", str(bn))
+    monkeypatch.setenv("MCG_TC_WMT", str(min(mt, 2)))
+    monkeypatch.setenv("MCG_TC_WBN", str(bn))
+    for case in (("shape3d", 3, 3, 64, 256, (7, 10, 10), (4, 4, 4), (1, 2, 2), (0, 1, 1)),     # 4*5*5*3 = 300 px: 3 boxes
+                 ("shape2d", 2, 11, 128, 256, (12, 12), (4, 4), (2, 2), (1, 1)),               # odd box counts per class
+                 ("shape_k3", 2, 5, 64, 256, (9, 9), (3, 3), (1, 1), (1, 1))):                 # 9 taps: odd slab count
+        run_conv_case(K, case, K.IMPL_TC, torch.bfloat16, TOL_BF16)
 
 
 def test_conv_tc_rejects_unsupported(K):
