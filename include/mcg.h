@@ -56,7 +56,7 @@ typedef struct {
  * impl = MCG_IMPL_SIMT: x/dy/dx/y of type `dtype`, w fp32.  impl = MCG_IMPL_TC: activations bf16, w bf16,
  *         requires Cin % 64 == 0 and Cout % 64 == 0 and stride in {1,2}.  out_dtype selects y / dx type.
  *         Layers with Cin <= 16 (the 3-channel image layers) are also taken: fprop/wgrad through an im2col
- *         matrix in `workspace`, dgrad through a narrow-N kernel with transposed weights in `workspace`.
+ *         matrix in `workspace`, dgrad as Z = dy . w^T (a tcgen05 GEMM into `workspace`) + a line-staged col2im.
  * mcg_conv_workspace_bytes: scratch the three calls need for this geometry (0 for the implicit-GEMM shapes). */
 size_t mcg_conv_workspace_bytes(const mcg_conv_geom* g, int impl);
 int mcg_conv_fprop(const mcg_conv_geom* g, const void* x, const void* w, const float* bias, void* y, int dtype,

@@ -1,15 +1,18 @@
 // tc_conv.cu — tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 in, fp32 accumulate).
 //
-// One warp-specialised kernel, three operand views over channels-last activations (C, W, H, T, N) and
-// (Cout, taps, Cin) weights:
-//   fprop : D[128 output pixels][BN cout]   += A(x box of tap j, 64 ci)  * B(w rows = cout, K-major)
-//   dgrad : D[128 input pixels of one stride class][BN cin] += A(dy box shifted by tap j, 64 co) * B(w, MN-major)
+// One PERSISTENT warp-specialised kernel (one CTA per SM), three operand views over channels-last activations
+// (C, W, H, T, N) and (Cout, taps, Cin) weights.  A CTA tile is MT blocks of 128 accumulator rows x BN columns:
+//   fprop : D[MT x 128 output pixels][BN cout] += A(x box of tap j, 64 ci)  * B(w rows = cout, K-major)
+//   dgrad : D[MT x 128 input pixels of one stride class][BN cin] += A(dy box shifted by tap j, 64 co) * B(w, MN-major)
 //           (stride-2 layers are decomposed into sH*sW parity classes, each a stride-1 conv over dy: no zero taps)
-//   wgrad : D[2 x 64 (tap,ci)][BN cout]     += A(x box, MN-major: K = 64 pixels) * B(dy box, MN-major), split over
-//           pixel boxes across CTAs, fp32 red.add into dw.
+//   wgrad : D[MT x 2 x 64 (tap,ci)][BN cout] += A(x box, MN-major: K = 64 pixels) * B(dy box, MN-major); the K loop
+//           (pixel boxes) of all tiles is one range cut evenly over the CTAs (stream-K), fp32 red.add into dw.
 // A tiles are 5-D TMA boxes (elementStrides carry the conv stride, out-of-bounds coordinates give the zero padding),
-// so no im2col buffer ever exists in HBM.  Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
-// warps 2-5 = epilogue (TMEM -> registers -> global).  Smem ring of STAGES x (16 KB A + BN*128 B B).
+// so no im2col buffer ever exists in HBM.  Roles: warp 0 = TMA producer (one elected thread), warp 1 = MMA issuer
+// (+ TMEM owner), warps 2-9 = epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter).  Shared-memory
+// ring of STAGES x (MT*16 KB A + BN*128 B B); accumulators double-buffered in TMEM when 2*MT*BN <= 512 columns, so the
+// epilogue of one tile overlaps the MMAs of the next.  Every CTA owns one contiguous range of work units (128-pixel
+// boxes for fprop/dgrad, K steps for wgrad), so the load imbalance is at most one unit.
 #include "common.cuh"
 #include "tc_prims.cuh"
 #include <map>

@@ -60,7 +60,7 @@ def workspace(nbytes, device):
 
 def tc_ok(g):
     """Shapes the tcgen05 path takes: 64-multiple channels (implicit GEMM) or <= 16 input channels (im2col GEMM /
-    narrow-N dgrad for the 3-channel image layers)."""
+    GEMM + col2im dgrad for the 3-channel image layers)."""
     if os.environ.get("MCG_DISABLE_TC"):   # debugging aid: route every convolution through the CUDA-core kernel
         return False
     if max(g.sT, g.sH, g.sW) > 2 or g.kT * g.kH * g.kW > 64 or g.Cout % 64:
