@@ -23,6 +23,10 @@ class _Config(object):
     enable_backprop = True
     # 'bf16': activations bf16, tcgen05 kernels where the shape allows; 'fp32': strict fp32 CUDA-core path
     compute_dtype = "bf16"
+    # True: every node remembers the CUDA stream its forward ran on and Variable.backward() replays its backward on the
+    # same stream, with events carrying the gradients across streams — independent branches of the step (real / fake
+    # clips, image / video discriminator, generator) then overlap on the device.  Set by the Updater.
+    branch_streams = False
 
 
 config = _Config()
@@ -160,6 +164,16 @@ class Variable(object):
                     memo[k] = any(needs(i) for i in v.creator_node.inputs)
             return memo[k]
 
+        # Branch concurrency: a node whose forward ran on stream s runs its backward on s; the gradient of a variable
+        # carries the (stream, event) pairs of the kernels that produced it, and a consumer on another stream waits
+        # for them.  Parameter gradients accumulate inside kernels (red.add / atomics), so only the caller has to wait
+        # for every stream used — done once at the end.
+        multi = config.branch_streams and torch.cuda.is_available()
+        home = torch.cuda.current_stream() if multi else None
+        ready = {}       # id(variable) -> [(stream, event)] of its gradient's producers
+        used = {}        # streams other than `home` that ran backward work
+        carry = []       # gradients that crossed streams: kept alive until every stream has been joined
+
         push(self.creator_node)
         while heap:
             _, _, node = heapq.heappop(heap)
@@ -170,7 +184,25 @@ class Variable(object):
             idx = tuple(i for i, x in enumerate(node.inputs) if needs(x))
             if not idx:
                 continue
-            gxs = node.backward(idx, gys)
+            if multi:
+                s = node.stream if node.stream is not None else home
+                for o, g in zip(outs, gys):
+                    if o is None or g is None:
+                        continue
+                    for (ps, ev) in ready.get(id(o), ()):
+                        if ps != s:
+                            s.wait_event(ev)
+                            carry.append(g)
+                    if id(o) not in ready and s != home:
+                        s.wait_stream(home)      # the seed gradient lives on the caller's stream
+                if s != home:
+                    used[s.cuda_stream] = s
+                with torch.cuda.stream(s):
+                    gxs = node.backward(idx, gys)
+                    ev = torch.cuda.Event()
+                    ev.record(s)
+            else:
+                gxs = node.backward(idx, gys)
             for i, gx in zip(idx, gxs):
                 if gx is None:
                     continue
@@ -180,6 +212,8 @@ class Variable(object):
                 else:
                     grads[id(x)] = _accumulate(grads.get(id(x)), gx)
                     keep[id(x)] = x
+                    if multi:
+                        ready.setdefault(id(x), []).append((s, ev))
                     if x.creator_node is None or retain_grad:
                         x._grad = grads[id(x)]
                 if x.creator_node is not None:
@@ -188,6 +222,11 @@ class Variable(object):
                 for o in outs:
                     if o is not None and o is not self:
                         grads.pop(id(o), None)
+                        ready.pop(id(o), None)
+        if multi:
+            for s in used.values():
+                home.wait_stream(s)
+            del carry
 
 
 class Parameter(Variable):
@@ -272,6 +311,7 @@ class FunctionNode(object):
     def __init__(self):
         self.inputs = ()
         self.outputs = ()
+        self.stream = None
         self.rank = 0
         self._retain_in = None
         self._retain_out = ()
@@ -288,6 +328,8 @@ class FunctionNode(object):
         ret = tuple(Variable(o, requires_grad=need) for o in outs)
         if need:
             self.inputs = inputs
+            # the stream this node's forward was enqueued on; backward() runs it there again (branch concurrency)
+            self.stream = torch.cuda.current_stream() if (config.branch_streams and torch.cuda.is_available()) else None
             self.rank = max([x.rank for x in inputs] + [0])
             for v in ret:
                 v.set_creator_node(self)

@@ -209,10 +209,12 @@ __global__ void __launch_bounds__(256) sum2_finalize(const float* partial, int n
   double s, q;
   warp_sum_partials(partial, nblk, C, c, s, q);
   if (threadIdx.x & 31) return;
-  if (out_a) out_a[c] = (accumulate ? out_a[c] : 0.f) + (float)s;
-  if (out_b) out_b[c] = (accumulate ? out_b[c] : 0.f) + (float)q;
-  if (acc_a) acc_a[c] += (float)s;
-  if (acc_b) acc_b[c] += (float)q;
+  // accumulating targets are parameter gradients: the real-clip and fake-clip branches of a pass may finish on two
+  // streams at once, so they are added atomically
+  if (out_a) { if (accumulate) atomicAdd(out_a + c, (float)s); else out_a[c] = (float)s; }
+  if (out_b) { if (accumulate) atomicAdd(out_b + c, (float)q); else out_b[c] = (float)q; }
+  if (acc_a) atomicAdd(acc_a + c, (float)s);
+  if (acc_b) atomicAdd(acc_b + c, (float)q);
 }
 
 // =====================================================================================================

@@ -89,40 +89,62 @@ class Updater(chainer.training.StandardUpdater):
         if self.model == 'cgan':
             x_real = self.concat_label_video(x_real, t_real)
         t = src.frame()                                   # updater.py:96, stays on the device
+        # Streams (additive): the step's independent branches run side by side — image discriminator on `di`, the
+        # generator on `g`, the video discriminator's fake-clip branch on `dvf`, its real-clip branch (and everything
+        # else) on the caller's stream.  Every FunctionNode remembers its stream, and Variable.backward() replays the
+        # node there (chainer.config.branch_streams), so e.g. pass B's real and fake chains interleave convolution
+        # kernels (tensor-bound) with BatchNorm / activation passes (HBM-bound) of the other chain.
         main = torch.cuda.current_stream()
-        side = main
         if self.use_streams:
             if self._side is None:
-                self._side = torch.cuda.Stream()
-            side = self._side
-            side.wait_stream(main)
-        with torch.cuda.stream(side):
-            y_real_i = image_dis(x_real, frame=t)         # updater.py:97   (side stream: ~30 small launches)
-        y_real_v = video_dis(x_real)                      # updater.py:98
+                self._side = {k: torch.cuda.Stream() for k in ("di", "g", "dvf")}
+            st_di, st_g, st_dvf = self._side["di"], self._side["g"], self._side["dvf"]
+        else:
+            st_di = st_g = st_dvf = main
+        old_branch = chainer.config.branch_streams
+        chainer.config.branch_streams = bool(self.use_streams)
+        try:
+            for s_ in {st_di, st_g, st_dvf} - {main}:
+                s_.wait_stream(main)
+            with torch.cuda.stream(st_di):
+                y_real_i = image_dis(x_real, frame=t)     # updater.py:97
+            y_real_v = video_dis(x_real)                  # updater.py:98
+            dv_real_done = torch.cuda.Event()
+            dv_real_done.record(main)
 
-        ## fake data
-        x_fake, t_fake = image_gen(batchsize)             # updater.py:101  (T,N,C,H,W)
-        x_fake = x_fake.transpose(1, 2, 0, 3, 4)          # updater.py:102  (N,C,T,H,W), still attached to G
-        t_fake = None if t_fake is None else Variable(t_fake, requires_grad=False)
-        if self.model == 'cgan':
-            raise NotImplementedError("cgan needs the label planes on the attached fake clip (SURVEY.md §8f rank 4)")
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            y_fake_i = image_dis(x_fake, frame=t)         # updater.py:107
-        y_fake_v = video_dis(x_fake)                      # updater.py:108
+            ## fake data
+            with torch.cuda.stream(st_g):
+                x_fake, t_fake = image_gen(batchsize)         # updater.py:101  (T,N,C,H,W)
+                x_fake = x_fake.transpose(1, 2, 0, 3, 4)      # updater.py:102  (N,C,T,H,W), still attached to G
+            t_fake = None if t_fake is None else Variable(t_fake, requires_grad=False)
+            if self.model == 'cgan':
+                raise NotImplementedError("cgan needs the label planes on the attached fake clip (SURVEY.md §8f rank 4)")
+            st_di.wait_stream(st_g)
+            with torch.cuda.stream(st_di):
+                y_fake_i = image_dis(x_fake, frame=t)     # updater.py:107
+            st_dvf.wait_stream(st_g)
+            st_dvf.wait_event(dv_real_done)               # BatchNorm running statistics: real call first, then fake
+            with torch.cuda.stream(st_dvf):
+                y_fake_v = video_dis(x_fake)              # updater.py:108
 
-        ## update  (updater.py:111-113)
-        # passes A, B: gradients flowing from the discriminator losses into the generator are discarded by the
-        # reference (image_gen.cleargrads() in pass C) -> not computed.  pass C: discriminator wgrads are discarded.
-        # Passes A and B touch disjoint parameters and activations, so A runs on the side stream while B runs on the
-        # main stream; both are complete before pass C reads the updated discriminator weights.
-        image_dis_optimizer.stop_variables = video_dis_optimizer.stop_variables = (x_fake,)
-        image_gen_optimizer.frozen_links = (image_dis, video_dis)
-        with torch.cuda.stream(side):
-            image_dis_optimizer.update(self.loss_dis, image_dis, y_real_i, y_fake_i, t_real, t_fake)
-        video_dis_optimizer.update(self.loss_dis, video_dis, y_real_v, y_fake_v, t_real, t_fake)
-        main.wait_stream(side)
-        image_gen_optimizer.update(self.loss_gen, image_gen, y_fake_i, y_fake_v, t_fake)
+            ## update  (updater.py:111-113)
+            # passes A, B: gradients flowing from the discriminator losses into the generator are discarded by the
+            # reference (image_gen.cleargrads() in pass C) -> not computed.  pass C: discriminator wgrads are discarded.
+            # Passes A and B touch disjoint parameters and activations, so A runs on `di` while B runs on the caller's
+            # stream (+ `dvf`); both are complete before pass C reads the updated discriminator weights.
+            image_dis_optimizer.stop_variables = video_dis_optimizer.stop_variables = (x_fake,)
+            image_gen_optimizer.frozen_links = (image_dis, video_dis)
+            with torch.cuda.stream(st_di):
+                image_dis_optimizer.update(self.loss_dis, image_dis, y_real_i, y_fake_i, t_real, t_fake)
+            main.wait_stream(st_dvf)
+            video_dis_optimizer.update(self.loss_dis, video_dis, y_real_v, y_fake_v, t_real, t_fake)
+            main.wait_stream(st_di)
+            main.wait_stream(st_g)
+            image_gen_optimizer.update(self.loss_gen, image_gen, y_fake_i, y_fake_v, t_fake)
+            for s_ in {st_di, st_g, st_dvf} - {main}:
+                main.wait_stream(s_)
+        finally:
+            chainer.config.branch_streams = old_branch
 
     # ------------------------------------------------------------------ update_core
     def _next_host_batch(self):
