@@ -204,6 +204,44 @@ def time_conv_layers(K, torch, peaks):
     return rows
 
 
+def gen_frames_per_s(torch, peaks, batch=256, video_len=32, iters=8):
+    """BASELINE config 5 (generate_samples inference): generator only, batch 256 clips of 32 frames, BatchNorm in
+    batch-statistics mode as generate_samples.py runs it, plus the uint8 / grid post-processing.  64x64 frames: the
+    reference's generator cannot emit 128x128 (net.py:115 hard-codes 64, 64)."""
+    from mocogan_chainer_b200 import chainer, generate_samples
+    from mocogan_chainer_b200 import random as mrandom
+    from mocogan_chainer_b200.model.net import ImageGenerator
+    chainer.config.compute_dtype = "bf16"
+    np.random.seed(0)
+    G = ImageGenerator(50, 10, 6, 3, 64, video_len)
+    G.arena()
+    mrandom.set_source(mrandom.DeviceRandom(seed=99, device="cuda", video_length=video_len))
+    src = mrandom.get_source()
+
+    def once():
+        src.begin_step()
+        return generate_samples.generate(G, batch, grid=True)
+
+    for _ in range(3):
+        once()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        u8, grid = once()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    frames = batch * video_len
+    gflop_per_frame = 116.82 / 560.0     # SURVEY.md App. C: generator forward 116.82 GF for 560 frames
+    return {"metric": "generator frames/s (generate_samples path: G forward + uint8/grid post-processing)",
+            "value": frames / ms * 1e3, "unit": "frames/s", "ms_per_batch": ms,
+            "config": {"workload": "BASELINE config 5 at the reference's native 64x64: generator only, batch %d clips x %d "
+                                   "frames, BatchNorm batch statistics, bf16" % (batch, video_len), "cuda_graph": False},
+            "achieved_tflops": frames * gflop_per_frame / ms, "frac_of_sustained_peak":
+            frames * gflop_per_frame / ms / peaks["bf16_sustained"]}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -261,7 +299,7 @@ def run_ours(args):
     assert K.tc_error_flag() == 0, "a tcgen05 kernel reported an mbarrier timeout"
     assert np.isfinite(loss_sink), "non-finite loss"
 
-    layer_rows, dominant, cpu = None, None, None
+    layer_rows, dominant, cpu, gen = None, None, None, None
     if rank == 0:
         layer_rows = time_conv_layers(K, torch, peaks)
         tot = {}
@@ -271,6 +309,7 @@ def run_ours(args):
         dominant = [r for r in layer_rows if (r["kernel"], r["layer"]) == dk][0]
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline_config1()
+        gen = gen_frames_per_s(torch, peaks) if world == 1 else None
     if rank != 0:
         return
     steps_per_s = world * args.steps / (ms_dev / 1e3)
@@ -303,6 +342,7 @@ def run_ours(args):
                               "tc_conv_ms_per_step_isolated": conv_ms},
                      "layers": layer_rows},
         "cpu_baseline": cpu,
+        "gen": gen,
     }
     print(json.dumps(line))
 

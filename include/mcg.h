@@ -117,6 +117,13 @@ int mcg_act_bn_bwd_apply(const void* g, const void* y, long long M, int C, int d
 int mcg_tanh_bwd_video(const void* gv, const void* gi, int g_dtype, const void* out_tn, int out_dtype, int N,
                        int T, int HW, int C, const int* frame_ptr, void* g_tn, int gout_dtype, void* stream);
 
+/* mcg_video_to_uint8: the sample post-processing of generate_samples.py:39 and util.py:30-51,100-101 in one pass over the
+ *   generator's output storage videos (T*N, H, W, C) (channels-last, tanh range): u8 (T, N, C, H, W) =
+ *   ((v / 2 + 0.5) * 255) truncated to uint8 and/or grid (T, C, size*H, size*W) = to_grid(u8, size) (cells beyond N
+ *   black).  Either output may be NULL.                                                                     */
+int mcg_video_to_uint8(const void* videos, int dtype, int T, int N, int C, int H, int W, unsigned char* u8,
+                       unsigned char* grid, int size, void* stream);
+
 /* ---- motion-code GRU (L.StatelessGRU, net.py:39-41,61-81) ----------------------------------------------
  * params: 12 device pointers in the order W_r.W,W_r.b,U_r.W,U_r.b,W_z.W,W_z.b,U_z.W,U_z.b,W.W,W.b,U.W,U.b
  *   (W_*: (H, L+H) row-major, U_*: (H,H)); labels int32[N] or NULL (L = 0); h0 (N,H); eps (T,N,H); zc (N,Zc).

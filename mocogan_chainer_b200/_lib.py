@@ -44,6 +44,7 @@ SIGNATURES = {
     "mcg_act_bn_bwd_reduce": (_i, [_p, _p, _ll, _i, _i, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p, _p, _sz, _p]),
     "mcg_act_bn_bwd_apply": (_i, [_p, _p, _ll, _i, _i, _p, _p, _p, _p, _p, _i, _f, _i, _p, _p, _p, _i, _p]),
     "mcg_tanh_bwd_video": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
+    "mcg_video_to_uint8": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "mcg_gru_forward": (_i, [C.POINTER(_p), _p, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "mcg_gru_backward": (_i, [C.POINTER(_p), C.POINTER(_p), _p, _i, _p, _p, _p, _i, _i, _i, _i, _p]),
     "mcg_loss_dis": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),

@@ -416,6 +416,32 @@ __global__ void __launch_bounds__(256) tanh_bwd_video_kernel(const TG* __restric
   }
 }
 
+// Generated clip -> uint8 pictures: videos (T*N, H, W, C) channels-last in tanh range (the generator's output storage)
+// -> u8 (T, N, C, H, W) = ((v / 2 + 0.5) * 255) truncated (generate_samples.py:39) and, when grid != NULL, the
+// size x size tiling of util.py:30-51 `to_grid` (T, C, size*H, size*W) in the same pass.
+template <typename T>
+__global__ void __launch_bounds__(256) video_to_uint8_kernel(const T* __restrict__ v, int Tn, int N, int C, int H, int W,
+                                                             unsigned char* __restrict__ u8, unsigned char* __restrict__ grid,
+                                                             int size) {
+  const long long total = (long long)Tn * N * C * H * W;
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    long long r = o;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H); r /= H;
+    const int c = (int)(r % C); r /= C;
+    const int n = (int)(r % N);
+    const int t = (int)(r / N);
+    const float x = ld<T>(v, ((((long long)t * N + n) * H + h) * W + w) * C + c);
+    const float y = (x / 2.f + 0.5f) * 255.f;
+    const unsigned char q = (unsigned char)(y < 0.f ? 0.f : (y > 255.f ? 255.f : y));   // truncation, as astype(uint8)
+    if (u8) u8[o] = q;
+    if (grid && n < size * size) {
+      const int gi = n / size, gj = n % size;
+      grid[(((long long)t * C + c) * (size * H) + gi * H + h) * (long long)(size * W) + gj * W + w] = q;
+    }
+  }
+}
+
 // =====================================================================================================
 // Adam + WeightDecay, casts, RNG utilities, step state
 // =====================================================================================================
@@ -662,6 +688,25 @@ int mcg_tanh_bwd_video(const void* gv, const void* gi, int g_dtype, const void* 
     });
   });
   MCG_CHECK_LAUNCH("mcg_tanh_bwd_video");
+  return 0;
+}
+
+int mcg_video_to_uint8(const void* videos, int dtype, int T, int N, int C, int H, int W, unsigned char* u8,
+                       unsigned char* grid, int size, void* stream) {
+  if (!videos || (!u8 && !grid) || T <= 0 || N <= 0 || C <= 0 || H <= 0 || W <= 0 || (grid && size <= 0))
+    MCG_FAIL(MCG_ERR_SHAPE, "mcg_video_to_uint8: bad arguments");
+  if (!dtype_ok(dtype)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_video_to_uint8: dtype");
+  cudaStream_t st = as_stream(stream);
+  const long long total = (long long)T * N * C * H * W;
+  if (grid) {   // cells beyond N stay black
+    cudaError_t e = cudaMemsetAsync(grid, 0, (size_t)T * C * size * H * size * W, st);
+    if (e != cudaSuccess) MCG_FAIL((int)e, "mcg_video_to_uint8: memset: %s", cudaGetErrorString(e));
+  }
+  dispatch1(dtype, [&](auto ti) {
+    using TI = decltype(ti);
+    video_to_uint8_kernel<TI><<<grid_for(total), 256, 0, st>>>((const TI*)videos, T, N, C, H, W, u8, grid, size);
+  });
+  MCG_CHECK_LAUNCH("mcg_video_to_uint8");
   return 0;
 }
 

@@ -3,7 +3,7 @@
 Positional args and flags are the reference's.  As in the reference the generator runs with chainer.config.train ==
 True, i.e. BatchNorm uses BATCH statistics at inference; dim_zl is inferred from the npz because the
 reference's default-constructed generator cannot load MUG-trained weights (App. B#10).  mp4/jpg writing needs ffmpeg
-(absent here): the uint8 videos (t, n, c, h, w) are saved as videos.npy instead."""
+(absent here): the uint8 videos (t, n, c, h, w) and the n x n grid video are saved as videos.npy / grid.npy instead."""
 import argparse
 import os
 import sys
@@ -28,12 +28,19 @@ def build_parser():
     return parser
 
 
-def generate(gen, num):
-    """videos = gen(num)[0].data; ((v / 2 + 0.5) * 255).astype(uint8)  — generate_samples.py:37-39."""
-    import torch
+def generate(gen, num, grid=True):
+    """videos = gen(num)[0].data; ((v / 2 + 0.5) * 255).astype(uint8) (generate_samples.py:37-39) and the n x n grid
+    video of util.py:30-51 (`to_grid`), both produced by ONE pass over the generator's output (mcg_video_to_uint8).
+    Returns (videos uint8 (t, bs, c, h, w), grid uint8 (t, c, n*h, n*w) | None)."""
+    from . import kernels as K
     with chainer.no_backprop_mode():
-        videos = gen(num)[0].data                       # (t, bs, c, h, w)
-    return ((videos.float() / 2. + 0.5) * 255).to(torch.uint8)
+        videos = gen(num)[0].data                       # (t, bs, c, h, w), a view of channels-last storage
+    t, bs, c, h, w = videos.shape
+    phys = videos.permute(0, 1, 3, 4, 2)                # (t, bs, h, w, c): the storage order
+    if not phys.is_contiguous():
+        phys = phys.contiguous()
+    n = int(round(np.sqrt(num)))
+    return K.video_to_uint8(phys.reshape(t * bs, 1, h, w, c), t, bs, True, n if grid else 0)
 
 
 def main(argv=None):
@@ -49,11 +56,13 @@ def main(argv=None):
                          n_filters=c8 // 8)
     chainer.serializers.load_npz(args.model_weight, gen)
     print(">>> generating...")
-    videos = generate(gen, args.num).cpu().numpy()
+    videos, grid = generate(gen, args.num)
+    videos, grid = videos.cpu().numpy(), grid.cpu().numpy()
     print(">>> saving...")
     save_path = Path(args.save_path)
     save_path.mkdir(parents=True, exist_ok=True)
     np.save(save_path / 'videos.npy', videos)
+    np.save(save_path / 'grid.npy', grid)               # (t, c, n*h, n*w): what the reference encodes as grid.mp4
     return videos
 
 

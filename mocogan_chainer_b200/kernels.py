@@ -164,6 +164,18 @@ def tanh_bwd_video(gv, gi, out_tn, N, T, HW, Cc, frame_ptr, g_tn):
                                    ptr(frame_ptr), ptr(g_tn), dt_code(g_tn), stream()), "mcg_tanh_bwd_video")
 
 
+def video_to_uint8(videos_phys, T, N, want_u8=True, grid_size=0):
+    """videos_phys: the generator's output storage (T*N, 1, H, W, C).  Returns (u8 (T,N,C,H,W) | None, grid | None)."""
+    B, _, H, W, Cc = videos_phys.shape
+    assert B == T * N and videos_phys.is_contiguous()
+    dev = videos_phys.device
+    u8 = torch.empty((T, N, Cc, H, W), dtype=torch.uint8, device=dev) if want_u8 else None
+    grid = torch.empty((T, Cc, grid_size * H, grid_size * W), dtype=torch.uint8, device=dev) if grid_size else None
+    check(lib().mcg_video_to_uint8(ptr(videos_phys), dt_code(videos_phys), T, N, Cc, H, W, ptr(u8), ptr(grid), int(grid_size),
+                                   stream()), "mcg_video_to_uint8")
+    return u8, grid
+
+
 def _ptr_array(tensors):
     arr = (C.c_void_p * len(tensors))()
     for i, t in enumerate(tensors):

@@ -379,3 +379,21 @@ def kink_margin(trace):
         bn = a[4]
         m = min(m, float(np.abs(bn).min() / np.sqrt(np.mean(bn * bn))))
     return m
+
+
+# ------------------------------------------------------------------------------------------------ sample post-processing
+def to_uint8(videos):
+    """generate_samples.py:39 / util.py:100-101: ((videos / 2. + 0.5) * 255).astype(np.uint8) — float -> uint8 by
+    truncation toward zero, videos (t, bs, c, h, w) in tanh range."""
+    return ((np.asarray(videos) / 2. + 0.5) * 255).astype(np.uint8)
+
+
+def to_grid(videos, size):
+    """util.py:30-51 `to_grid`: (t, bs, c, h, w) uint8 -> (t, c, size*h, size*w); videos beyond bs are black."""
+    t, bs, c, h, w = videos.shape
+    grid = np.zeros((t, c, size * h, size * w), dtype=videos.dtype)
+    for i in range(size):
+        for j in range(size):
+            if i * size + j < bs:
+                grid[:, :, i * h:i * h + h, j * w:j * w + w] = videos[:, i * size + j]
+    return grid

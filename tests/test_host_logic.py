@@ -149,3 +149,18 @@ def test_model_wiring_follows_train_py():
     assert di.in_channels == 9 and dv.in_channels == 9
     with pytest.raises(ValueError):
         build_models("cgan", 50, 10, 0, 3, 8, 16, True, 0.2)
+
+
+def test_oracle_to_grid_restates_util_py():
+    """oracle.to_uint8 / to_grid against a literal transcription of the reference's arithmetic on a small case
+    (util.py:30-51: blank videos appended, cell (i, j) = video i*size + j; generate_samples.py:39)."""
+    import numpy as np
+    from oracle import mocogan_ref as ref
+    rng = np.random.default_rng(0)
+    v = np.tanh(rng.standard_normal((2, 3, 1, 2, 2)))
+    u = ref.to_uint8(v)
+    assert u.dtype == np.uint8 and u.min() >= 0 and np.array_equal(u, ((v / 2. + 0.5) * 255).astype(np.uint8))
+    g = ref.to_grid(u, 2)
+    assert g.shape == (2, 1, 4, 4)
+    assert np.array_equal(g[:, :, 0:2, 2:4], u[:, 1]) and np.array_equal(g[:, :, 2:4, 0:2], u[:, 2])
+    assert (g[:, :, 2:4, 2:4] == 0).all()          # the fourth cell has no video: black

@@ -33,6 +33,25 @@ def test_train_then_generate(tmp_path, monkeypatch):
     videos = generate_samples.main([str(out / "image_gen_epoch_fianl.npz"), str(tmp_path / "gen"), "-n", "4"])
     assert videos.shape == (16, 4, 3, 64, 64) and videos.dtype == np.uint8
     assert os.path.exists(tmp_path / "gen" / "videos.npy")
+    from oracle import mocogan_ref as ref
+    grid = np.load(tmp_path / "gen" / "grid.npy")
+    assert grid.shape == (16, 3, 128, 128) and np.array_equal(grid, ref.to_grid(videos, 2))   # util.py:30-51
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_video_to_uint8_and_grid_match_reference_postprocessing(dtype):
+    """generate_samples.py:39 `((v / 2. + 0.5) * 255).astype(np.uint8)` + util.py:30-51 `to_grid`, bit-exact (5 videos on
+    a 3x3 grid: four cells stay black; values hit both ends of the tanh range)."""
+    from mocogan_chainer_b200 import kernels as K
+    from oracle import mocogan_ref as ref
+    T, N, C, H, W = 3, 5, 3, 8, 8
+    v = torch.tanh(torch.randn((T, N, C, H, W), generator=torch.Generator().manual_seed(0)) * 2).to(dtype)
+    v.view(-1)[:4] = torch.tensor([-1.0, 1.0, 0.0, 0.999], dtype=dtype)
+    phys = v.cuda().permute(0, 1, 3, 4, 2).contiguous().reshape(T * N, 1, H, W, C)
+    u8, grid = K.video_to_uint8(phys, T, N, True, 3)
+    want = ref.to_uint8(v.float().numpy())
+    assert np.array_equal(u8.cpu().numpy(), want)
+    assert np.array_equal(grid.cpu().numpy(), ref.to_grid(want, 3))
 
 
 def test_graph_replay_equals_eager_with_same_seed():
