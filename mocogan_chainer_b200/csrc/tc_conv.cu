@@ -865,6 +865,75 @@ __global__ void __launch_bounds__(128) col2im_line_kernel(const __nv_bfloat16* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Narrow-Cin data gradient as ONE stride-1 convolution over dy ("merged classes").  With ti = sT*l + e, hi = sH*i + a,
+// wi = sW*j + b the taps that reach class (e,a,b) read dy at (l+dt, i+dh, j+dw) for a small window of offsets that is
+// the same for every class, so
+//   Zm[n,l,i,j][(e,a,b,ci)] = sum_{dt,dh,dw,co} dy[n,l+dt,i+dh,j+dw,co] * Wm[(e,a,b,ci)][(dt,dh,dw)][co]
+// is an ordinary fprop with 64 (padded) output columns, where Wm holds w[co,kt,kh,kw,ci] at the offsets that class uses
+// and zeros elsewhere; dx is Zm with its column blocks spread back over the stride grid (depth-to-space).  dy is read
+// window-size times from L2 and nothing of size M x taps*Cin ever exists (the Z = dy.w^T + col2im form wrote and re-read
+// 179 MB for Dv.dc1).
+struct MergedGeom {
+  int Cin, Cout, kT, kH, kW, sT, sH, sW, pT, pH, pW;
+  int nT, nH, nW;            // window extents (offsets dmin .. dmin+n-1)
+  int dt_min, dh_min, dw_min;
+};
+// Wm[row = ((e*sH + a)*sW + b)*Cin + ci (zero rows up to 64)][tap' = (u*nH + v)*nW + q][co]
+__global__ void merged_weights_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wm, MergedGeom G) {
+  const int taps2 = G.nT * G.nH * G.nW;
+  const long long total = 64LL * taps2 * G.Cout;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % G.Cout);
+    long long r = idx / G.Cout;
+    const int tap2 = (int)(r % taps2);
+    const int row = (int)(r / taps2);
+    __nv_bfloat16 val = __float2bfloat16_rn(0.f);
+    if (row < G.sT * G.sH * G.sW * G.Cin) {
+      const int ci = row % G.Cin;
+      int cls = row / G.Cin;
+      const int b = cls % G.sW; cls /= G.sW;
+      const int a = cls % G.sH;
+      const int e = cls / G.sH;
+      const int q = tap2 % G.nW, v = (tap2 / G.nW) % G.nH, u = tap2 / (G.nW * G.nH);
+      const int kt = e + G.pT - G.sT * (u + G.dt_min), kh = a + G.pH - G.sH * (v + G.dh_min), kw = b + G.pW - G.sW * (q + G.dw_min);
+      if (kt >= 0 && kt < G.kT && kh >= 0 && kh < G.kH && kw >= 0 && kw < G.kW)
+        val = w[((((long long)co * G.kT + kt) * G.kH + kh) * G.kW + kw) * G.Cin + ci];
+    }
+    wm[idx] = val;
+  }
+}
+// dx[n,ti,hi,wi,ci] = bias[ci] + Zm[n, ti/sT, hi/sH, wi/sW][((ti%sT*sH + hi%sH)*sW + wi%sW)*Cin + ci]
+__global__ void __launch_bounds__(256) depth_to_space_kernel(const __nv_bfloat16* __restrict__ zm, const float* __restrict__ bias,
+                                                             void* __restrict__ dx, int out_f32, long long pixels, int Cin, int Ti,
+                                                             int Hi, int Wi, int L, int I, int J, int sT, int sH, int sW) {
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < pixels; pix += (long long)gridDim.x * blockDim.x) {
+    long long r = pix;
+    const int wi = (int)(r % Wi); r /= Wi;
+    const int hi = (int)(r % Hi); r /= Hi;
+    const int ti = (int)(r % Ti);
+    const long long n = r / Ti;
+    const int cls = ((ti % sT) * sH + hi % sH) * sW + wi % sW;
+    const __nv_bfloat16* src = zm + ((((n * L + ti / sT) * I + hi / sH) * (long long)J + wi / sW) * 64 + cls * Cin);
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float v = __bfloat162float(src[ci]) + (bias ? bias[ci] : 0.f);
+      if (out_f32) reinterpret_cast<float*>(dx)[pix * Cin + ci] = v;
+      else reinterpret_cast<__nv_bfloat16*>(dx)[pix * Cin + ci] = __float2bfloat16_rn(v);
+    }
+  }
+}
+static int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+static bool merged_geom(const mcg_conv_geom* g, MergedGeom* G) {
+  if (g->sT * g->sH * g->sW * g->Cin > 64) return false;
+  *G = MergedGeom{g->Cin, g->Cout, g->kT, g->kH, g->kW, g->sT, g->sH, g->sW, g->pT, g->pH, g->pW, 0, 0, 0, 0, 0, 0};
+  // offsets d = (phase + p - k) / s over phases 0..s-1 and taps 0..k-1 (only exact divisions are real taps, the
+  // window just has to cover them)
+  G->dt_min = floor_div(g->pT - (g->kT - 1), g->sT); G->nT = floor_div(g->sT - 1 + g->pT, g->sT) - G->dt_min + 1;
+  G->dh_min = floor_div(g->pH - (g->kH - 1), g->sH); G->nH = floor_div(g->sH - 1 + g->pH, g->sH) - G->dh_min + 1;
+  G->dw_min = floor_div(g->pW - (g->kW - 1), g->sW); G->nW = floor_div(g->sW - 1 + g->pW, g->sW) - G->dw_min + 1;
+  return G->nT * G->nH * G->nW <= 64;
+}
+
 static long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 
 bool tc_small_supported(const mcg_conv_geom* g) {
@@ -874,7 +943,14 @@ bool tc_small_supported(const mcg_conv_geom* g) {
 size_t tc_small_workspace(const mcg_conv_geom* g) {
   const long long M = (long long)g->N * g->To * g->Ho * g->Wo;
   const long long K = (long long)g->kT * g->kH * g->kW * g->Cin, Kp = round_up(K, 64);
-  return (size_t)(round_up(M * Kp * 2, 1024) + round_up((long long)g->Cout * Kp * 2, 1024) + 4096);
+  size_t need = (size_t)(round_up(M * Kp * 2, 1024) + round_up((long long)g->Cout * Kp * 2, 1024) + 4096);
+  MergedGeom G;
+  if (merged_geom(g, &G)) {   // dgrad: Zm (one 64-column row per stride cell) + the merged weights
+    const long long cells = (long long)g->N * ceil_div(g->Ti, g->sT) * ceil_div(g->Hi, g->sH) * ceil_div(g->Wi, g->sW);
+    const size_t merged = (size_t)(round_up(cells * 128, 1024) + round_up(64LL * G.nT * G.nH * G.nW * g->Cout * 2, 1024) + 4096);
+    if (merged > need) need = merged;
+  }
+  return need;
 }
 
 int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b, void* out, const float* bias, int out_dtype,
@@ -892,6 +968,25 @@ int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b
   if (mode == kDgrad) {
     // a = dy (N,To,Ho,Wo,Cout), b = w bf16 (Cout,taps,Cin), out = dx (N,Ti,Hi,Wi,Cin):
     //   Z[M][Kp] = dy[M][Cout] . wt[Kp][Cout]^T  (tcgen05 GEMM over the line of M output pixels), then col2im.
+    MergedGeom G;
+    if (merged_geom(g, &G) && !getenv("MCG_NO_MERGED_DGRAD")) {
+      const int L = ceil_div(g->Ti, g->sT), I = ceil_div(g->Hi, g->sH), J = ceil_div(g->Wi, g->sW);
+      const long long cells = (long long)g->N * L * I * J;
+      __nv_bfloat16* zm = reinterpret_cast<__nv_bfloat16*>(base);
+      __nv_bfloat16* wm = reinterpret_cast<__nv_bfloat16*>(base + round_up(cells * 128, 1024));
+      merged_weights_kernel<<<128, 256, 0, st>>>((const __nv_bfloat16*)b, wm, G);
+      MCG_CHECK_LAUNCH(who);
+      // stride-1 fprop over dy: "input" = dy, window (nT,nH,nW), zero padding -dmin (the far side is TMA out-of-bounds fill)
+      mcg_conv_geom g2 = {g->N, g->Cout, 64, g->To, g->Ho, g->Wo, L, I, J, G.nT, G.nH, G.nW, 1, 1, 1, -G.dt_min, -G.dh_min, -G.dw_min};
+      if ((rc = tc_conv(kFprop, &g2, a, wm, zm, nullptr, MCG_BF16, st))) return rc;
+      const long long pixels = (long long)g->N * g->Ti * g->Hi * g->Wi;
+      long long nb = (pixels + 255) / 256;
+      if (nb > (long long)num_sms() * 16) nb = (long long)num_sms() * 16;
+      depth_to_space_kernel<<<(unsigned)nb, 256, 0, st>>>(zm, bias, out, out_dtype == MCG_F32, pixels, g->Cin, g->Ti, g->Hi, g->Wi,
+                                                         L, I, J, g->sT, g->sH, g->sW);
+      MCG_CHECK_LAUNCH(who);
+      return 0;
+    }
     if (M > 0x7fffffffLL) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: too many pixels", who);
     transpose_jk_kernel<<<64, 256, 0, st>>>((const __nv_bfloat16*)b, wpad, g->Cout, K, Kp);
     MCG_CHECK_LAUNCH(who);
