@@ -31,6 +31,11 @@ enum { MCG_IMPL_SIMT = 0, MCG_IMPL_TC = 1 };          /* fp32 CUDA-core path | t
 /* OR-ed into `impl` for fprop/wgrad of a layer with Cin <= 16: the workspace already holds this x's im2col matrix
  * (written by an earlier fprop/wgrad call on the same x and geometry), so it is not rebuilt. */
 #define MCG_FLAG_COLS_VALID 0x100
+/* OR-ed into `impl` (tcgen05 path): the weight tensor w — and dw — has only n < g->Cout rows, because the tensor that
+ * carries g->Cout channels (dy, or y for fprop) was zero-padded to a multiple of 64 channels by the caller
+ * (the generator's first layer has 60 = dim_zc + dim_zm input channels, net.py:31,44).  Rows n..Cout-1 read as zero,
+ * the matching columns of dw are not written, and fprop must not be given a bias. */
+#define MCG_W_ROWS(n) (((n) & 0xffff) << 16)
 enum { MCG_ERR_SHAPE = -1, MCG_ERR_UNSUPPORTED = -2, MCG_ERR_WORKSPACE = -3, MCG_ERR_DRIVER = -4 };
 
 int mcg_version(void);

@@ -146,6 +146,17 @@ class ConvolutionND(FunctionNode):
             in_sp = tuple(ss * (i - 1) + kk - 2 * pp for i, kk, ss, pp in zip((T, H, Wd), k, s, p))
             g = K.make_geom(N, ish[-1], ish[0], in_sp, k, s, p)  # the conv whose dgrad this deconv is
             out_sp, Cout = in_sp, ish[-1]
+        self.w_rows = 0
+        if self.deconv and config.compute_dtype == "bf16" and xp.dtype == torch.bfloat16 and Cx % 64 and not K.tc_ok(g):
+            # the generator's first layer: 60 = dim_zc + dim_zm input channels (net.py:31,44).  The latent is zero-padded
+            # to 64 channels so the layer runs on tcgen05; the weight keeps its 60 rows (MCG_W_ROWS: the missing rows are
+            # TMA zero fill, the matching dw columns are never written).
+            Cp = (Cx + 63) // 64 * 64
+            gp = K.make_geom(N, ish[-1], Cp, in_sp, k, s, p)
+            if K.tc_ok(gp):
+                xpad = torch.zeros((N, T, H, Wd, Cp), dtype=xp.dtype, device=xp.device)
+                xpad[..., :Cx].copy_(xp)
+                xp, g, self.w_rows = xpad, gp, Cx
         self.g = g
         self.impl = K.IMPL_TC if (config.compute_dtype == "bf16" and xp.dtype == torch.bfloat16 and K.tc_ok(g)) else K.IMPL_SIMT
         w = W.bstore if self.impl == K.IMPL_TC else W.store
@@ -158,7 +169,7 @@ class ConvolutionND(FunctionNode):
             if config.enable_backprop:
                 self.cols_ws = ws   # small-Cin layers: keep x's im2col matrix for wgrad
         else:
-            K.conv_dgrad(g, xp, w, bias, y, self.impl)
+            K.conv_dgrad(g, xp, w, bias, y, self.impl | K.w_rows(self.w_rows))
         self.xp = xp
         return logical_view(y, nd),
 
@@ -169,18 +180,21 @@ class ConvolutionND(FunctionNode):
         w = W.bstore if self.impl == K.IMPL_TC else W.store
         gx = None
         ws = None
+        wr = K.w_rows(self.w_rows)
         if 0 in idx:
             dx = torch.empty_like(self.xp)
             if not self.deconv:
                 K.conv_dgrad(g, gyp, w, None, dx, self.impl)
             else:
-                ws = K.conv_fprop(g, gyp, w, None, dx, self.impl)
+                ws = K.conv_fprop(g, gyp, w, None, dx, self.impl | wr)
+            if self.w_rows:
+                dx = dx[..., :self.w_rows]      # the padded channels carry no gradient
             gx = logical_view(dx, self.nd)
         if 1 in idx:
             if not self.deconv:
                 K.conv_wgrad(g, self.xp, gyp, W.gstore, self.impl, ws=self.cols_ws, cols_valid=self.cols_ws is not None)
             else:
-                K.conv_wgrad(g, gyp, self.xp, W.gstore, self.impl, ws=ws, cols_valid=ws is not None)
+                K.conv_wgrad(g, gyp, self.xp, W.gstore, self.impl | wr, ws=ws, cols_valid=ws is not None)
         self.cols_ws = None
         if 2 in idx and b is not None and self.bias_grad:
             gb_src = as_physical(gys[0])  # original precision: the fp32 loss gradient of the last layer cancels heavily

@@ -49,6 +49,7 @@ struct TcParams {
   long long total_units, units_per_cta;
   int total_boxes;                                            // wgrad: K steps per tile
   int total_slabs, kreal;                                     // wgrad: valid 64-row slabs; real row length of dw
+  int wrows;                                                  // real rows of w / dw (< Cout when the channels were padded)
   int debug_skip_epi;
   int out_f32, ocols;                                        // ocols = channels of one output pixel row
   int planar_chunk, planar_cols;   // fprop: write column c to plane c/chunk as [plane][pixel][chunk] (0 = row-major)
@@ -374,7 +375,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
             }
             if (row_ok) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) atomicAdd(dw + (long long)(ncol0 + c0 + i) * P.kreal + kidx, __uint_as_float(v[i]));
+              for (int i = 0; i < 32; ++i)
+                if (ncol0 + c0 + i < P.wrows) atomicAdd(dw + (long long)(ncol0 + c0 + i) * P.kreal + kidx, __uint_as_float(v[i]));
             }
           }
         }
@@ -572,7 +574,7 @@ bool tc_supported(const mcg_conv_geom* g) {
 }
 
 int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void* out, const float* bias, int out_dtype,
-            cudaStream_t st, int kreal = 0, int planar_chunk = 0, int planar_cols = 0) {
+            cudaStream_t st, int kreal = 0, int planar_chunk = 0, int planar_cols = 0, int wrows = 0) {
   const char* who = mode == kFprop ? "mcg_conv_fprop(tc)" : mode == kDgrad ? "mcg_conv_dgrad(tc)" : "mcg_conv_wgrad(tc)";
   if (!tc_supported(g)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: needs Cin,Cout %% 64 == 0, stride <= 2, <= 64 taps", who);
   TcParams P;
@@ -583,6 +585,11 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
   P.planar_chunk = planar_chunk;
   P.planar_cols = planar_cols;
   P.planar_stride = (long long)g->Wo * planar_chunk;   // planar mode is only used on 1-D line geometries (M = Wo)
+  // wrows < Cout: the weight tensor has fewer rows than the (zero-padded) channel count of the activations it meets —
+  // rows beyond are TMA out-of-bounds zero fill, columns of dw beyond are not written
+  if (wrows <= 0 || wrows > g->Cout) wrows = g->Cout;
+  if (wrows < g->Cout && mode == kFprop && bias) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: bias with padded weight rows", who);
+  P.wrows = wrows;
   if (planar_chunk) {
     if (planar_chunk % 4 || planar_cols > 256) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: planar chunk %d / cols %d", who, planar_chunk, planar_cols);
     for (int c = 0; c < planar_cols; c += 4) {
@@ -615,7 +622,7 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
     P.ntn = g->Cout / cfg.bn;
     P.ntiles = P.ntn;
     const int grid = split_units(P, (long long)P.ntiles * P.nboxes, 1);
-    uint64_t d2[2] = {(uint64_t)P.Ktot, (uint64_t)g->Cout}, s2[1] = {(uint64_t)P.Ktot * 2};
+    uint64_t d2[2] = {(uint64_t)P.Ktot, (uint64_t)wrows}, s2[1] = {(uint64_t)P.Ktot * 2};
     uint32_t b2[2] = {64, (uint32_t)cfg.bn}, e2[2] = {1, 1};
     if ((rc = get_map(&mb, b, 2, d2, s2, b2, e2))) return rc;
     return launch_tc_cfg<kFprop>(cfg, ma, mb, P, grid, out, bias, st, who);
@@ -661,7 +668,7 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
     P.ntn = g->Cin / cfg.bn;
     P.ntiles = ncls * P.ntn;
     const int grid = split_units(P, (long long)P.ntiles * P.nboxes, 1);
-    uint64_t d2[2] = {(uint64_t)P.Ktot, (uint64_t)g->Cout}, s2[1] = {(uint64_t)P.Ktot * 2};
+    uint64_t d2[2] = {(uint64_t)P.Ktot, (uint64_t)wrows}, s2[1] = {(uint64_t)P.Ktot * 2};
     uint32_t b2[2] = {64, 64}, e2[2] = {1, 1};
     if ((rc = get_map(&mb, b, 2, d2, s2, b2, e2))) return rc;
     return launch_tc_cfg<kDgrad>(cfg, ma, mb, P, grid, out, bias, st, who);
@@ -1053,27 +1060,31 @@ int mcg_conv_fprop(const mcg_conv_geom* g, const void* x, const void* w, const f
                    int out_dtype, int impl, void* workspace, size_t workspace_bytes, void* stream) {
   if (!g || !x || !w || !y) MCG_FAIL(MCG_ERR_SHAPE, "mcg_conv_fprop: null pointer");
   const bool cols_valid = (impl & MCG_FLAG_COLS_VALID) != 0;
+  const int wrows = (impl >> 16) & 0xffff;
   impl &= 0xff;
   if (impl == MCG_IMPL_TC) {
     if (dtype != MCG_BF16) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_fprop(tc): activations must be bf16");
     if (!tc_supported(g) && tc_small_supported(g))
       return tc_conv_small(0, g, x, w, y, bias, out_dtype, workspace, workspace_bytes, as_stream(stream), cols_valid);
-    return tc_conv(0, g, x, w, y, bias, out_dtype, as_stream(stream));
+    return tc_conv(0, g, x, w, y, bias, out_dtype, as_stream(stream), 0, 0, 0, wrows);
   }
+  if (wrows) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_fprop: MCG_W_ROWS needs MCG_IMPL_TC");
   return simt_conv(0, g, x, nullptr, (const float*)w, bias, y, dtype, out_dtype, 0, as_stream(stream));
 }
 
 int mcg_conv_dgrad(const mcg_conv_geom* g, const void* dy, const void* w, const float* bias, void* dx, int dtype,
                    int out_dtype, int accumulate, int impl, void* workspace, size_t workspace_bytes, void* stream) {
   if (!g || !dy || !w || !dx) MCG_FAIL(MCG_ERR_SHAPE, "mcg_conv_dgrad: null pointer");
+  const int wrows = (impl >> 16) & 0xffff;
   impl &= 0xff;
   if (impl == MCG_IMPL_TC) {
     if (dtype != MCG_BF16) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_dgrad(tc): activations must be bf16");
     if (accumulate) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_dgrad(tc): accumulate not supported");
     if (!tc_supported(g) && tc_small_supported(g))
       return tc_conv_small(1, g, dy, w, dx, bias, out_dtype, workspace, workspace_bytes, as_stream(stream), false);
-    return tc_conv(1, g, dy, w, dx, bias, out_dtype, as_stream(stream));
+    return tc_conv(1, g, dy, w, dx, bias, out_dtype, as_stream(stream), 0, 0, 0, wrows);
   }
+  if (wrows) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_dgrad: MCG_W_ROWS needs MCG_IMPL_TC");
   return simt_conv(1, g, dy, nullptr, (const float*)w, bias, dx, dtype, out_dtype, accumulate, as_stream(stream));
 }
 
@@ -1081,12 +1092,14 @@ int mcg_conv_wgrad(const mcg_conv_geom* g, const void* x, const void* dy, float*
                    size_t workspace_bytes, void* stream) {
   if (!g || !x || !dy || !dw) MCG_FAIL(MCG_ERR_SHAPE, "mcg_conv_wgrad: null pointer");
   const bool cols_valid = (impl & MCG_FLAG_COLS_VALID) != 0;
+  const int wrows = (impl >> 16) & 0xffff;
   impl &= 0xff;
+  if (wrows && impl != MCG_IMPL_TC) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_wgrad: MCG_W_ROWS needs MCG_IMPL_TC");
   if (impl == MCG_IMPL_TC) {
     if (dtype != MCG_BF16) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_wgrad(tc): activations must be bf16");
     if (!tc_supported(g) && tc_small_supported(g))
       return tc_conv_small(2, g, x, dy, dw, nullptr, MCG_F32, workspace, workspace_bytes, as_stream(stream), cols_valid);
-    return tc_conv(2, g, x, dy, dw, nullptr, MCG_F32, as_stream(stream));
+    return tc_conv(2, g, x, dy, dw, nullptr, MCG_F32, as_stream(stream), 0, 0, 0, wrows);
   }
   return simt_conv(2, g, dy, x, nullptr, nullptr, dw, dtype, MCG_F32, 1, as_stream(stream));
 }

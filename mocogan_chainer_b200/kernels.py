@@ -79,6 +79,11 @@ def _conv_ws(g, impl, device):
 COLS_VALID = 0x100
 
 
+def w_rows(n):
+    """MCG_W_ROWS(n): the weight tensor has only n rows, fewer than the (zero-padded) channel count (0 = no padding)."""
+    return (int(n) & 0xffff) << 16
+
+
 def conv_fprop(g, x, w, bias, y, impl, ws=None, cols_valid=False):
     """ws: optional caller-held workspace (kept alive to reuse the im2col of a small-Cin layer in wgrad)."""
     if ws is None:

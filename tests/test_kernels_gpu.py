@@ -155,6 +155,37 @@ def test_conv_tcgen05_every_tile_shape(K, mt, bn, monkeypatch):
         run_conv_case(K, case, K.IMPL_TC, torch.bfloat16, TOL_BF16)
 
 
+def test_conv_tc_padded_weight_rows(K):
+    """MCG_W_ROWS: the generator's first layer (60 = dim_zc + dim_zm channels, net.py:44) on tcgen05 — dy is zero-padded
+    to 64 channels, the weight / dw keep 60 rows; compared with the oracle convolution that has Cout = 60."""
+    rng = np.random.default_rng(5)
+    N, Cin, Cout, Cp = 70, 128, 60, 64
+    x = bf16_round(rng.standard_normal((N, Cin, 4, 4)))
+    W = bf16_round(rng.standard_normal((Cout, Cin, 4, 4)) * 0.1)
+    gy = bf16_round(rng.standard_normal((N, Cout, 1, 1)))
+    y_ref = ops.conv_nd_fwd(x, W, None, (1, 1), (0, 0))
+    gx_ref, gW_ref, _ = ops.conv_nd_bwd(x, W, gy, (1, 1), (0, 0))
+    g = K.make_geom(N, Cin, Cp, (1, 4, 4), (1, 4, 4), (1, 1, 1), (0, 0, 0))
+    wr = K.w_rows(Cout)
+    xd = to_cl(x, torch.bfloat16)
+    gyd = torch.zeros((N, 1, 1, 1, Cp), dtype=torch.bfloat16, device="cuda")
+    gyd[..., :Cout] = to_cl(gy, torch.bfloat16)
+    wd = w_to_internal(W, torch.bfloat16)                       # 60 rows
+    yd = torch.full((N, 1, 1, 1, Cp), 7.0, dtype=torch.bfloat16, device="cuda")
+    K.conv_fprop(g, xd, wd, None, yd, K.IMPL_TC | wr)
+    dxd = torch.empty_like(xd)
+    K.conv_dgrad(g, gyd, wd, None, dxd, K.IMPL_TC | wr)
+    guard = torch.full((Cout + 4,) + tuple(wd.shape[1:]), 3.0, dtype=torch.float32, device="cuda")
+    guard[:Cout] = 0
+    K.conv_wgrad(g, xd, gyd, guard, K.IMPL_TC | wr)             # rows 60..63 of the buffer must stay untouched
+    torch.cuda.synchronize()
+    assert K.tc_error_flag() == 0
+    assert relerr(from_cl(yd[..., :Cout], 2), y_ref) < TOL_BF16 and float(yd[..., Cout:].abs().max()) == 0.0
+    assert relerr(from_cl(dxd, 2), gx_ref) < TOL_BF16
+    assert relerr(w_from_internal(guard[:Cout]), gW_ref) < TOL_BF16
+    assert float((guard[Cout:] - 3.0).abs().max()) == 0.0
+
+
 def test_conv_tc_rejects_unsupported(K):
     from mocogan_chainer_b200._lib import McgError
     g = K.make_geom(2, 24, 64, (1, 16, 16), (1, 4, 4), (1, 2, 2), (0, 1, 1))   # 24 channels: neither path takes it
