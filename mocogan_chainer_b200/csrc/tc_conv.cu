@@ -910,22 +910,31 @@ __global__ void merged_weights_kernel(const __nv_bfloat16* __restrict__ w, __nv_
     wm[idx] = val;
   }
 }
-// dx[n,ti,hi,wi,ci] = bias[ci] + Zm[n, ti/sT, hi/sH, wi/sW][((ti%sT*sH + hi%sH)*sW + wi%sW)*Cin + ci]
+// dx[n,ti,hi,wi,ci] = bias[ci] + Zm[n, ti/sT, hi/sH, wi/sW][((ti%sT*sH + hi%sH)*sW + wi%sW)*Cin + ci].
+// One thread per (cell, e, a): the sW*Cin values of classes (e, a, 0..sW-1) are contiguous in the Zm row AND in dx
+// (sW neighbouring pixels of one line), so the thread moves one short contiguous run.
 __global__ void __launch_bounds__(256) depth_to_space_kernel(const __nv_bfloat16* __restrict__ zm, const float* __restrict__ bias,
-                                                             void* __restrict__ dx, int out_f32, long long pixels, int Cin, int Ti,
+                                                             void* __restrict__ dx, int out_f32, long long cells, int Cin, int Ti,
                                                              int Hi, int Wi, int L, int I, int J, int sT, int sH, int sW) {
-  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < pixels; pix += (long long)gridDim.x * blockDim.x) {
-    long long r = pix;
-    const int wi = (int)(r % Wi); r /= Wi;
-    const int hi = (int)(r % Hi); r /= Hi;
-    const int ti = (int)(r % Ti);
-    const long long n = r / Ti;
-    const int cls = ((ti % sT) * sH + hi % sH) * sW + wi % sW;
-    const __nv_bfloat16* src = zm + ((((n * L + ti / sT) * I + hi / sH) * (long long)J + wi / sW) * 64 + cls * Cin);
-    for (int ci = 0; ci < Cin; ++ci) {
-      const float v = __bfloat162float(src[ci]) + (bias ? bias[ci] : 0.f);
-      if (out_f32) reinterpret_cast<float*>(dx)[pix * Cin + ci] = v;
-      else reinterpret_cast<__nv_bfloat16*>(dx)[pix * Cin + ci] = __float2bfloat16_rn(v);
+  const int RUN = sW * Cin, sub = sT * sH;
+  const long long total = cells * sub;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ea = (int)(idx % sub);
+    long long r = idx / sub;
+    const int j = (int)(r % J); r /= J;
+    const int i = (int)(r % I); r /= I;
+    const int l = (int)(r % L);
+    const long long n = r / L;
+    const int e = ea / sH, a = ea % sH;
+    const int ti = l * sT + e, hi = i * sH + a, wi0 = j * sW;
+    if (ti >= Ti || hi >= Hi) continue;
+    const __nv_bfloat16* src = zm + (idx / sub) * 64 + ea * RUN;
+    const long long dst = (((n * Ti + ti) * Hi + hi) * (long long)Wi + wi0) * Cin;
+    for (int q = 0; q < RUN; ++q) {
+      if (wi0 + q / Cin >= Wi) break;
+      const float v = __bfloat162float(src[q]) + (bias ? bias[q % Cin] : 0.f);
+      if (out_f32) reinterpret_cast<float*>(dx)[dst + q] = v;
+      else reinterpret_cast<__nv_bfloat16*>(dx)[dst + q] = __float2bfloat16_rn(v);
     }
   }
 }
@@ -986,10 +995,9 @@ int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b
       // stride-1 fprop over dy: "input" = dy, window (nT,nH,nW), zero padding -dmin (the far side is TMA out-of-bounds fill)
       mcg_conv_geom g2 = {g->N, g->Cout, 64, g->To, g->Ho, g->Wo, L, I, J, G.nT, G.nH, G.nW, 1, 1, 1, -G.dt_min, -G.dh_min, -G.dw_min};
       if ((rc = tc_conv(kFprop, &g2, a, wm, zm, nullptr, MCG_BF16, st))) return rc;
-      const long long pixels = (long long)g->N * g->Ti * g->Hi * g->Wi;
-      long long nb = (pixels + 255) / 256;
+      long long nb = (cells * g->sT * g->sH + 255) / 256;
       if (nb > (long long)num_sms() * 16) nb = (long long)num_sms() * 16;
-      depth_to_space_kernel<<<(unsigned)nb, 256, 0, st>>>(zm, bias, out, out_dtype == MCG_F32, pixels, g->Cin, g->Ti, g->Hi, g->Wi,
+      depth_to_space_kernel<<<(unsigned)nb, 256, 0, st>>>(zm, bias, out, out_dtype == MCG_F32, cells, g->Cin, g->Ti, g->Hi, g->Wi,
                                                          L, I, J, g->sT, g->sH, g->sW);
       MCG_CHECK_LAUNCH(who);
       return 0;
