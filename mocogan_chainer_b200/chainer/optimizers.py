@@ -14,6 +14,10 @@ class Adam(Optimizer):
         self.grad_scale = 1.0
         self.frozen_links = ()       # links whose parameter gradients are dead work in this pass
         self.stop_variables = ()     # variables backward must not pass while this optimizer updates
+        # additive: stream for the gradient all-reduce + Adam kernel (None = the caller's).  Whoever reads the updated
+        # weights next must be ordered after it; the Updater puts the video discriminator's update on the stream of the
+        # only branch that needs it before the end of the step.
+        self.update_stream = None
 
     def setup(self, link):
         super(Adam, self).setup(link)
@@ -53,16 +57,25 @@ class Adam(Optimizer):
                     v.stop = False
             del loss
         arena = self.target.arena()
-        if self.grad_transform is not None:
-            self.grad_transform(arena.grad)
         wd = 0.0
         for h in self._hooks.values():
             if isinstance(h, WeightDecay):
                 wd += h.rate
         self.t += 1
-        K.int_add(self.t_dev, 1)
-        K.adam_step(arena.data, arena.grad, self.m, self.v, arena.bf16, self.alpha, self.beta1, self.beta2, self.eps, wd,
-                    self.grad_scale, self.t_dev)
+
+        def apply():
+            if self.grad_transform is not None:
+                self.grad_transform(arena.grad)
+            K.int_add(self.t_dev, 1)
+            K.adam_step(arena.data, arena.grad, self.m, self.v, arena.bf16, self.alpha, self.beta1, self.beta2, self.eps,
+                        wd, self.grad_scale, self.t_dev)
+
+        if self.update_stream is not None and torch.cuda.is_available():
+            self.update_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.update_stream):
+                apply()
+        else:
+            apply()
 
     def serialize(self, serializer):
         serializer("t", (self, "t"))

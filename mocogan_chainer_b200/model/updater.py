@@ -137,6 +137,9 @@ class Updater(chainer.training.StandardUpdater):
             with torch.cuda.stream(st_di):
                 image_dis_optimizer.update(self.loss_dis, image_dis, y_real_i, y_fake_i, t_real, t_fake)
             main.wait_stream(st_dvf)
+            # the video discriminator's all-reduce + Adam go on `dvf`: in pass C only the Dv branch (which runs there)
+            # needs the updated weights, so the image-discriminator branch of pass C starts under them
+            video_dis_optimizer.update_stream = st_dvf if self.use_streams else None
             video_dis_optimizer.update(self.loss_dis, video_dis, y_real_v, y_fake_v, t_real, t_fake)
             main.wait_stream(st_di)
             main.wait_stream(st_g)
