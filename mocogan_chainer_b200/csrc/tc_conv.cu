@@ -374,9 +374,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
               tmem_ld_wait();
             }
             if (row_ok) {
+              float* dst = dw + (long long)(ncol0 + c0) * P.kreal + kidx;
+              if (ncol0 + c0 + 32 <= P.wrows) {   // the common case, warp-uniform: no per-column test
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (ncol0 + c0 + i < P.wrows) atomicAdd(dw + (long long)(ncol0 + c0 + i) * P.kreal + kidx, __uint_as_float(v[i]));
+                for (int i = 0; i < 32; ++i) atomicAdd(dst + (long long)i * P.kreal, __uint_as_float(v[i]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (ncol0 + c0 + i < P.wrows) atomicAdd(dst + (long long)i * P.kreal, __uint_as_float(v[i]));
+              }
             }
           }
         }
