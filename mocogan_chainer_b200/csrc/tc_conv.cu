@@ -50,6 +50,11 @@ struct TcParams {
   int total_boxes;                                            // wgrad: K steps per tile
   int total_slabs, kreal;                                     // wgrad: valid 64-row slabs; real row length of dw
   int wrows;                                                  // real rows of w / dw (< Cout when the channels were padded)
+  // temporal tap re-use (tc_conv_tr_kernel): a tap GROUP = the tr_kT temporal taps that share (kh,kw); taps[] then
+  // lists groups (dt = first frame of the halo box, kidx = tap index of kt = 0)
+  int tr_kT, tr_kstep, tr_rev;       // taps per group; tap-index step between kt and kt+1; 1 = tap kt reads frame offset kT-1-kt
+  int tr_frame_bytes, tr_ablock_bytes;   // bytes of one frame of a block (R rows) / of one block's halo box ((BT+kT-1)*R rows)
+  int tr_aslots, tr_bslots;
   int debug_skip_epi;
   int out_f32, ocols;                                        // ocols = channels of one output pixel row
   int planar_chunk, planar_cols;   // fprop: write column c to plane c/chunk as [plane][pixel][chunk] (0 = row-major)
@@ -110,6 +115,131 @@ __device__ __forceinline__ TcBox tc_decode_box(const TcParams& P, int bi) {
   b.t0 = (bi % P.nbt) * P.BT; bi /= P.nbt;
   b.n0 = bi * P.BB;
   return b;
+}
+
+// Epilogue role (warps 2-9), shared by the kernels below: walks the same segment sequence as the producer / MMA roles,
+// waits for an accumulator buffer, moves TMEM -> registers -> global, and hands the buffer back.
+// A lone warp per scheduler runs the epilogue's dependent instruction chains at a fraction of the issue rate, so two
+// warps share each TMEM lane quarter and take alternate 32-column chunks.
+template <int MODE, int BN, int MT, int NBUF>
+__device__ __forceinline__ void tc_epilogue_role(const TcParams& P, void* __restrict__ out, const float* __restrict__ bias,
+                                                 uint32_t tmem, uint32_t tfull_a, uint32_t tempty_a, int warp, int lane, int* err) {
+  constexpr int ACC_COLS = MT * BN;
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;  // accumulator row == TMEM lane
+    TcSegIter<MODE, MT> iter(P);
+    TcSeg sg;
+    uint32_t seg = 0;
+    while (iter.next(P, sg)) {
+      const int nt = sg.tile % P.ntn, mg = sg.tile / P.ntn;
+      const int ncol0 = nt * BN;
+      const bool have_acc = sg.nk > 0;
+      const uint32_t buf = seg % NBUF;
+      if (have_acc) {
+        if (!mbar_wait_a(tfull_a + buf * 8, (seg / NBUF) & 1, err)) break;
+        tc_fence_after();
+      }
+      const uint32_t acc = tmem + (uint32_t(q * 32) << 16) + buf * ACC_COLS;
+      if (MODE != kWgrad) {
+        const int cls = mg;
+        const int pw = cls % P.cls_w, phh = (cls / P.cls_w) % P.cls_h, pt = cls / (P.cls_w * P.cls_h);
+        int rr = r;
+        const int iw = rr % P.BW; rr /= P.BW;
+        const int ih = rr % P.BH; rr /= P.BH;
+        const int itt = rr % P.BT; rr /= P.BT;
+        const int ib = rr;
+#pragma unroll 1
+        for (int m = 0; m < sg.nlive; ++m) {
+          const TcBox bx = tc_decode_box(P, sg.box0 + m);
+          const int ow = (bx.w0 + iw) * P.o_mul_w + pw, oh = (bx.h0 + ih) * P.o_mul_h + phh, ot = (bx.t0 + itt) * P.o_mul_t + pt;
+          const int on = bx.n0 + ib;
+          const bool valid = ow < P.full_w && oh < P.full_h && ot < P.full_t && on < P.EN;
+          const long long base = (long long)on * P.os_n + (long long)ot * P.os_t + (long long)oh * P.os_h + (long long)ow * P.os_w + ncol0;
+#pragma unroll 1
+          for (int c0 = half * 32; c0 < BN; c0 += 64) {
+            uint32_t v[32];
+            if (have_acc) {
+              tmem_ld32(acc + m * BN + c0, v);
+              tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0u;
+            }
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + (bias ? bias[ncol0 + c0 + i] : 0.f);
+            if (valid) {
+              if (MODE == kFprop && P.planar_chunk) {
+                // planar bf16 output for the narrow-Cin dgrad GEMM: plane = (kt,kh) run, so col2im reads contiguous lines
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const int c = ncol0 + c0 + i;
+                  if (c < P.planar_cols) {
+                    const int plane = P.planar_plane[c >> 2], within = P.planar_within[c >> 2];
+                    uint2 u;
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(f[i], f[i + 1]), hi = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
+                    u.x = *reinterpret_cast<uint32_t*>(&lo);
+                    u.y = *reinterpret_cast<uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(o + plane * P.planar_stride + (long long)ow * P.planar_chunk + within) = u;
+                  }
+                }
+              } else if (P.out_f32) {
+                float* o = reinterpret_cast<float*>(out) + base + c0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+              } else {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + base + c0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                  uint4 u;
+                  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+                  h[0] = __floats2bfloat162_rn(f[i], f[i + 1]);
+                  h[1] = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
+                  h[2] = __floats2bfloat162_rn(f[i + 4], f[i + 5]);
+                  h[3] = __floats2bfloat162_rn(f[i + 6], f[i + 7]);
+                  *reinterpret_cast<uint4*>(o + i) = u;
+                }
+              }
+            }
+          }
+        }
+      } else {
+        float* dw = reinterpret_cast<float*>(out);
+#pragma unroll 1
+        for (int m = 0; m < MT; ++m) {
+          const int u = (mg * MT + m) * 2 + (r >> 6);
+          const bool live = u < P.total_slabs;
+          const TcTap tp = P.taps[live ? u / P.chunks : 0];
+          const long long kidx = (long long)tp.kidx * P.Cin + (u % P.chunks) * 64 + (r & 63);
+          const bool row_ok = live && kidx < P.kreal && have_acc && !P.debug_skip_epi;
+#pragma unroll 1
+          for (int c0 = half * 32; c0 < BN; c0 += 64) {
+            uint32_t v[32];
+            if (have_acc) {
+              tmem_ld32(acc + m * BN + c0, v);
+              tmem_ld_wait();
+            }
+            if (row_ok) {
+              float* dst = dw + (long long)(ncol0 + c0) * P.kreal + kidx;
+              if (ncol0 + c0 + 32 <= P.wrows) {   // the common case, warp-uniform: no per-column test
+#pragma unroll
+                for (int i = 0; i < 32; ++i) atomicAdd(dst + (long long)i * P.kreal, __uint_as_float(v[i]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (ncol0 + c0 + i < P.wrows) atomicAdd(dst + (long long)i * P.kreal, __uint_as_float(v[i]));
+              }
+            }
+          }
+        }
+      }
+      if (have_acc) {
+        tc_fence_before();
+        mbar_arrive_a(tempty_a + buf * 8);   // 128 arrivals release the accumulator buffer to the MMA issuer
+        ++seg;
+      }
+    }
 }
 
 template <int MODE, int BN, int MT, int STAGES>
@@ -276,123 +406,166 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     }
   } else {
     // ================================================= epilogue ============================================
-    // A lone warp per scheduler runs the epilogue's dependent instruction chains at a fraction of the issue rate, so two
-    // warps share each TMEM lane quarter and take alternate 32-column chunks.
-    const int q = warp & 3, half = (warp - 2) >> 2;
-    const int r = q * 32 + lane;  // accumulator row == TMEM lane
-    TcSegIter<MODE, MT> iter(P);
-    TcSeg sg;
-    uint32_t seg = 0;
-    while (iter.next(P, sg)) {
-      const int nt = sg.tile % P.ntn, mg = sg.tile / P.ntn;
-      const int ncol0 = nt * BN;
-      const bool have_acc = sg.nk > 0;
-      const uint32_t buf = seg % NBUF;
-      if (have_acc) {
-        if (!mbar_wait_a(tfull_a + buf * 8, (seg / NBUF) & 1, err)) break;
-        tc_fence_after();
-      }
-      const uint32_t acc = tmem + (uint32_t(q * 32) << 16) + buf * ACC_COLS;
-      if (MODE != kWgrad) {
-        const int cls = mg;
-        const int pw = cls % P.cls_w, phh = (cls / P.cls_w) % P.cls_h, pt = cls / (P.cls_w * P.cls_h);
-        int rr = r;
-        const int iw = rr % P.BW; rr /= P.BW;
-        const int ih = rr % P.BH; rr /= P.BH;
-        const int itt = rr % P.BT; rr /= P.BT;
-        const int ib = rr;
-#pragma unroll 1
-        for (int m = 0; m < sg.nlive; ++m) {
-          const TcBox bx = tc_decode_box(P, sg.box0 + m);
-          const int ow = (bx.w0 + iw) * P.o_mul_w + pw, oh = (bx.h0 + ih) * P.o_mul_h + phh, ot = (bx.t0 + itt) * P.o_mul_t + pt;
-          const int on = bx.n0 + ib;
-          const bool valid = ow < P.full_w && oh < P.full_h && ot < P.full_t && on < P.EN;
-          const long long base = (long long)on * P.os_n + (long long)ot * P.os_t + (long long)oh * P.os_h + (long long)ow * P.os_w + ncol0;
-#pragma unroll 1
-          for (int c0 = half * 32; c0 < BN; c0 += 64) {
-            uint32_t v[32];
-            if (have_acc) {
-              tmem_ld32(acc + m * BN + c0, v);
-              tmem_ld_wait();
-            } else {
+    tc_epilogue_role<MODE, BN, MT, NBUF>(P, out, bias, tmem, tfull_a, tempty_a, warp, lane, err);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// =============================================================================================================
+// Temporal tap re-use (video discriminator, kT = 4, sT = 1).  The kT taps that share (kh, kw) read the SAME pixels of kT
+// consecutive frame windows, so ONE TMA box of BT + kT - 1 frames (pixel box (BW, BH, BT, 1), R = BW*BH rows per frame,
+// R % 8 == 0) serves all of them: tap kt is the same shared-memory tile entered R*128*offset(kt) bytes further in — a
+// whole number of 1024-byte swizzle atoms, so only the descriptor start address moves.  A traffic from L2 drops by
+// kT*BT / (BT + kT - 1) (1.6x for BT = 2, 2.3x for BT = 4, 2.9x for BT = 8), which is what bounds the N = 64 / 128
+// layers.  Two rings: halo boxes (one per group x 64-channel chunk, MT blocks) and weight tiles (one per K step).
+// =============================================================================================================
+constexpr int kTrMaxASlots = 4, kTrMaxBSlots = 8;
+template <int MODE, int BN, int MT>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_conv_tr_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                   const __grid_constant__ CUtensorMap mapB,
+                                                                   const __grid_constant__ TcParams P, void* __restrict__ out,
+                                                                   const float* __restrict__ bias) {
+  static_assert(MODE == kFprop || MODE == kDgrad, "temporal re-use is for fprop / dgrad");
+  constexpr int B_BYTES = BN * 128;
+  constexpr int ACC_COLS = MT * BN;
+  constexpr int NBUF = (2 * ACC_COLS <= 512) ? 2 : 1;
+  constexpr int TMEM_NEED = NBUF * ACC_COLS;
+  constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : (TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512)));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t fullA[kTrMaxASlots], emptyA[kTrMaxASlots], fullB[kTrMaxBSlots], emptyB[kTrMaxBSlots], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* err = &g_tc_error;
+  const int ASLOTS = P.tr_aslots, BSLOTS = P.tr_bslots;
+  const int aslot_bytes = MT * P.tr_ablock_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTrMaxASlots; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < kTrMaxBSlots; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiThreads); }
+    fence_barrier_init();
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1) { tmem_alloc(&tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t ringA = smem_u32(smem), ringB = ringA + ASLOTS * aslot_bytes;
+  const uint32_t fullA_a = smem_u32(&fullA[0]), emptyA_a = smem_u32(&emptyA[0]);
+  const uint32_t fullB_a = smem_u32(&fullB[0]), emptyB_a = smem_u32(&emptyB[0]);
+  const uint32_t tfull_a = smem_u32(&tfull_bar[0]), tempty_a = smem_u32(&tempty_bar[0]);
+  const int KT = P.tr_kT;
+
+  if (warp == 0) {
+    // ================================================= TMA producer =========================================
+    if (elect_one()) {
+      const uint64_t map_a = reinterpret_cast<uint64_t>(&mapA), map_b = reinterpret_cast<uint64_t>(&mapB);
+      TcSegIter<MODE, MT> iter(P);
+      TcSeg sg;
+      int sa = 0, sb = 0;
+      uint32_t pha = 1, phb = 1;
+      bool alive = true;
+      while (alive && iter.next(P, sg)) {
+        const int nt = sg.tile % P.ntn, cls = sg.tile / P.ntn;
+        const int ncol0 = nt * BN;
+        TcBox bx[MT];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = 0u;
-            }
-            float f[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + (bias ? bias[ncol0 + c0 + i] : 0.f);
-            if (valid) {
-              if (MODE == kFprop && P.planar_chunk) {
-                // planar bf16 output for the narrow-Cin dgrad GEMM: plane = (kt,kh) run, so col2im reads contiguous lines
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  const int c = ncol0 + c0 + i;
-                  if (c < P.planar_cols) {
-                    const int plane = P.planar_plane[c >> 2], within = P.planar_within[c >> 2];
-                    uint2 u;
-                    __nv_bfloat162 lo = __floats2bfloat162_rn(f[i], f[i + 1]), hi = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
-                    u.x = *reinterpret_cast<uint32_t*>(&lo);
-                    u.y = *reinterpret_cast<uint32_t*>(&hi);
-                    *reinterpret_cast<uint2*>(o + plane * P.planar_stride + (long long)ow * P.planar_chunk + within) = u;
-                  }
-                }
-              } else if (P.out_f32) {
-                float* o = reinterpret_cast<float*>(out) + base + c0;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-              } else {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + base + c0;
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                  uint4 u;
-                  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-                  h[0] = __floats2bfloat162_rn(f[i], f[i + 1]);
-                  h[1] = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
-                  h[2] = __floats2bfloat162_rn(f[i + 4], f[i + 5]);
-                  h[3] = __floats2bfloat162_rn(f[i + 6], f[i + 7]);
-                  *reinterpret_cast<uint4*>(o + i) = u;
-                }
-              }
-            }
-          }
-        }
-      } else {
-        float* dw = reinterpret_cast<float*>(out);
-#pragma unroll 1
         for (int m = 0; m < MT; ++m) {
-          const int u = (mg * MT + m) * 2 + (r >> 6);
-          const bool live = u < P.total_slabs;
-          const TcTap tp = P.taps[live ? u / P.chunks : 0];
-          const long long kidx = (long long)tp.kidx * P.Cin + (u % P.chunks) * 64 + (r & 63);
-          const bool row_ok = live && kidx < P.kreal && have_acc && !P.debug_skip_epi;
-#pragma unroll 1
-          for (int c0 = half * 32; c0 < BN; c0 += 64) {
-            uint32_t v[32];
-            if (have_acc) {
-              tmem_ld32(acc + m * BN + c0, v);
-              tmem_ld_wait();
-            }
-            if (row_ok) {
-              float* dst = dw + (long long)(ncol0 + c0) * P.kreal + kidx;
-              if (ncol0 + c0 + 32 <= P.wrows) {   // the common case, warp-uniform: no per-column test
+          bx[m] = tc_decode_box(P, sg.box0 + (m < sg.nlive ? m : 0));
+          bx[m].w0 = bx[m].w0 * P.a_mul_w + P.a_add_w;
+          bx[m].h0 = bx[m].h0 * P.a_mul_h + P.a_add_h;
+          bx[m].t0 = bx[m].t0 * P.a_mul_t + P.a_add_t;
+        }
+        const uint32_t txa = sg.nlive * P.tr_ablock_bytes;
+        const int j_end = P.tap_begin[cls] + P.tap_count[cls], chunks = P.chunks;
+        for (int j = P.tap_begin[cls]; alive && j < j_end; ++j) {
+          const TcTap tp = P.taps[j];
+          for (int c = 0; alive && c < chunks; ++c) {
+            if (!mbar_wait_a(emptyA_a + sa * 8, pha, err)) { alive = false; break; }
+            mbar_expect_tx_a(fullA_a + sa * 8, txa);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) atomicAdd(dst + (long long)i * P.kreal, __uint_as_float(v[i]));
+            for (int m = 0; m < MT; ++m)
+              if (m < sg.nlive)
+                tma_load_5d_a(ringA + sa * aslot_bytes + m * P.tr_ablock_bytes, map_a, fullA_a + sa * 8, c * 64, bx[m].w0 + tp.dw,
+                              bx[m].h0 + tp.dh, bx[m].t0 + tp.dt, bx[m].n0);
+            if (++sa == ASLOTS) { sa = 0; pha ^= 1; }
+            for (int kt = 0; kt < KT; ++kt) {
+              if (!mbar_wait_a(emptyB_a + sb * 8, phb, err)) { alive = false; break; }
+              mbar_expect_tx_a(fullB_a + sb * 8, B_BYTES);
+              const int kcol = (tp.kidx + kt * P.tr_kstep) * P.Cin;
+              if (MODE == kFprop) {
+                tma_load_2d_a(ringB + sb * B_BYTES, map_b, fullB_a + sb * 8, kcol + c * 64, ncol0);
               } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (ncol0 + c0 + i < P.wrows) atomicAdd(dst + (long long)i * P.kreal, __uint_as_float(v[i]));
+                for (int sl = 0; sl < BN / 64; ++sl)
+                  tma_load_2d_a(ringB + sb * B_BYTES + sl * 8192, map_b, fullB_a + sb * 8, kcol + ncol0 + sl * 64, c * 64);
               }
+              if (++sb == BSLOTS) { sb = 0; phb ^= 1; }
             }
           }
         }
       }
-      if (have_acc) {
-        tc_fence_before();
-        mbar_arrive(&tempty_bar[buf]);   // 128 arrivals release the accumulator buffer to the MMA issuer
+    }
+  } else if (warp == 1) {
+    // ================================================= MMA issuer ===========================================
+    if (elect_one()) {
+      constexpr int B_MN = (MODE != kFprop);
+      constexpr uint32_t B_KSTEP = (B_MN ? 2048 : 32) >> 4;
+      const uint32_t idesc = make_idesc_bf16(128, BN, 0, B_MN);
+      const uint32_t desc_hi = smem_desc_hi(1024);
+      const uint32_t a_lo0 = smem_desc_lo(ringA, 16), b_lo0 = smem_desc_lo(ringB, B_MN ? 8192 : 16);
+      const uint32_t ablock16 = P.tr_ablock_bytes >> 4, aslot16 = aslot_bytes >> 4, frame16 = P.tr_frame_bytes >> 4;
+      TcSegIter<MODE, MT> iter(P);
+      TcSeg sg;
+      uint32_t seg = 0, pha = 0, phb = 0;
+      int sa = 0, sb = 0;
+      bool alive = true;
+      while (alive && iter.next(P, sg)) {
+        const int cls = sg.tile / P.ntn;
+        const int ngc = P.tap_count[cls] * P.chunks;   // group x chunk steps
+        if (ngc == 0) continue;
+        const uint32_t buf = seg % NBUF;
+        if (!mbar_wait_a(tempty_a + buf * 8, ((seg / NBUF) & 1) ^ 1, err)) break;
+        tc_fence_after();
+        const uint32_t acc = tmem + buf * ACC_COLS;
+        const int nlive = sg.nlive;
+        uint32_t first = 1;
+        for (int gc = 0; alive && gc < ngc; ++gc) {
+          if (!mbar_wait_a(fullA_a + sa * 8, pha, err)) { alive = false; break; }
+          tc_fence_after();
+          const uint32_t a_slot = a_lo0 + sa * aslot16;
+          for (int kt = 0; kt < KT; ++kt) {
+            if (!mbar_wait_a(fullB_a + sb * 8, phb, err)) { alive = false; break; }
+            tc_fence_after();
+            const uint32_t a_tap = a_slot + (P.tr_rev ? (KT - 1 - kt) : kt) * frame16;
+            const uint32_t b_lo = b_lo0 + sb * (B_BYTES >> 4);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+              if (m >= nlive) break;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_lh(acc + m * BN, a_tap + m * ablock16 + k * 2, desc_hi, b_lo + k * B_KSTEP, desc_hi, idesc,
+                             (first && k == 0) ? 0u : 1u);
+            }
+            first = 0;
+            umma_commit_a(emptyB_a + sb * 8);
+            if (++sb == BSLOTS) { sb = 0; phb ^= 1; }
+          }
+          umma_commit_a(emptyA_a + sa * 8);
+          if (++sa == ASLOTS) { sa = 0; pha ^= 1; }
+        }
+        if (alive) umma_commit_a(tfull_a + buf * 8);
         ++seg;
       }
     }
+  } else {
+    // ================================================= epilogue ============================================
+    tc_epilogue_role<MODE, BN, MT, NBUF>(P, out, bias, tmem, tfull_a, tempty_a, warp, lane, err);
   }
   tc_fence_before();
   __syncthreads();
@@ -503,7 +676,7 @@ static double step_cycles(int mt, int bn, long long active_ctas) {
   const double ld = bytes / share;
   return ld > mma ? ld : mma;
 }
-static TileCfg pick_tile(int mode, long long nboxes, int ncls, int cols, int nk) {
+static TileCfg pick_tile(int mode, long long nboxes, int ncls, int cols, int nk, double* cost_out = nullptr) {
   const int fm = tc_env_int("MCG_TC_MT"), fb = tc_env_int("MCG_TC_BN");
   const int sms = num_sms();
   TileCfg best{1, 64};
@@ -526,6 +699,7 @@ static TileCfg pick_tile(int mode, long long nboxes, int ncls, int cols, int nk)
       if (cost < best_cost) { best_cost = cost; best = TileCfg{mt, bn}; }
     }
   }
+  if (cost_out) *cost_out = best_cost;
   return best;
 }
 // cut `units` into equal contiguous ranges, one per CTA
@@ -569,6 +743,95 @@ static int launch_tc_cfg(TileCfg c, const CUtensorMap& ma, const CUtensorMap& mb
   if (MODE == kFprop) { MCG_TC_CASE(192, 1); MCG_TC_CASE(192, 2); }
 #undef MCG_TC_CASE
   MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: tile %dx%d", who, c.mt * 128, c.bn);
+}
+
+// ---- temporal tap re-use: plan and launch ---------------------------------------------------------------------
+struct TrPlan {
+  bool ok;
+  Box bx;                 // (BW, BH, BT, 1)
+  int mt, bn, aslots, bslots;
+  double cost;
+};
+// E* = extents the 128-pixel boxes tile, groups = (kh,kw) tap groups per class (max), KT temporal taps per group
+static TrPlan plan_tr(int EW, int EH, int ET, int N, int cols, int ncls, int groups, int chunks, int KT) {
+  TrPlan best;
+  best.ok = false;
+  best.cost = 1e300;
+  const int sms = num_sms();
+  const double chip_bw = 7400.0, sm_cap = 110.0;
+  const int fm = tc_env_int("MCG_TC_MT"), fb = tc_env_int("MCG_TC_BN"), fr = tc_env_int("MCG_TC_TR_R");
+  for (int bw = 1; bw <= 64; bw *= 2)
+    for (int bh = 1; bw * bh <= 64; bh *= 2) {
+      const int R = bw * bh;
+      if (R < 16 || (fr && R != fr)) continue;                 // R % 8 == 0 and BT = 128 / R <= 8
+      const int bt = 128 / R;
+      const long long nboxes = (long long)ceil_div(EW, bw) * ceil_div(EH, bh) * ceil_div(ET, bt) * N;
+      const int ablock = (bt + KT - 1) * R * 128;
+      const int bns[3] = {256, 128, 64};
+      for (int bi = 0; bi < 3; ++bi) {
+        const int bn = bns[bi];
+        if (cols % bn || (fb && bn != fb && cols % fb == 0)) continue;
+        for (int mt = 4; mt >= 1; mt /= 2) {
+          if (mt * bn > 256 || (fm && mt != fm)) continue;     // keep the accumulators double-buffered
+          const int bbytes = bn * 128;
+          int aslots = 2;
+          long long left = 220 * 1024 - (long long)aslots * mt * ablock;
+          if (left < 3LL * bbytes) continue;
+          int bslots = (int)(left / bbytes);
+          if (bslots > kTrMaxBSlots) bslots = kTrMaxBSlots;
+          left -= (long long)bslots * bbytes;
+          while (aslots < kTrMaxASlots && left >= (long long)mt * ablock) { ++aslots; left -= (long long)mt * ablock; }
+          const long long units = (long long)ncls * (cols / bn) * nboxes;
+          const long long ctas = units < sms ? units : sms;
+          const long long upc = (units + ctas - 1) / ctas;
+          const long long steps = (upc + mt - 1) / mt;
+          double share = chip_bw / (double)ctas;
+          if (share > sm_cap) share = sm_cap;
+          const double bytes = (double)mt * ablock + (double)KT * bbytes, mma = (double)KT * 2.0 * mt * bn;
+          const double stepc = bytes / share > mma ? bytes / share : mma;
+          const double cost = (double)steps * ((double)groups * chunks * stepc + 300.0) + mt * bn * 6.0;
+          if (cost < best.cost) {
+            best.ok = true; best.bx = Box{bw, bh, bt, 1}; best.mt = mt; best.bn = bn; best.aslots = aslots; best.bslots = bslots;
+            best.cost = cost;
+          }
+        }
+      }
+    }
+  return best;
+}
+template <int MODE, int BN, int MT>
+static int launch_tr(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, int grid, void* out, const float* bias,
+                     cudaStream_t st, const char* who) {
+  const size_t smem = (size_t)P.tr_aslots * MT * P.tr_ablock_bytes + (size_t)P.tr_bslots * BN * 128 + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_tr_kernel<MODE, BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) MCG_FAIL((int)e, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
+    configured = smem;
+  }
+  tc_conv_tr_kernel<MODE, BN, MT><<<grid, kTcThreads, smem, st>>>(ma, mb, P, out, bias);
+  MCG_CHECK_LAUNCH(who);
+  return 0;
+}
+template <int MODE>
+static int launch_tr_cfg(int bn, int mt, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, int grid, void* out,
+                         const float* bias, cudaStream_t st, const char* who) {
+#define MCG_TR_CASE(bn_, mt_) \
+  if (bn == bn_ && mt == mt_) return launch_tr<MODE, bn_, mt_>(ma, mb, P, grid, out, bias, st, who)
+  MCG_TR_CASE(64, 1); MCG_TR_CASE(64, 2); MCG_TR_CASE(64, 4);
+  MCG_TR_CASE(128, 1); MCG_TR_CASE(128, 2);
+  MCG_TR_CASE(256, 1);
+#undef MCG_TR_CASE
+  MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: temporal re-use tile %dx%d", who, mt * 128, bn);
+}
+// MCG_TC_TR=1 switches the temporal re-use kernel on (whenever the geometry allows).  It is OFF by default: measured on
+// B200 it halves the L2 -> SM bytes of Dv.dc2 dgrad (2.18 -> 1.11 GB, ncu) yet runs 0.132 -> 0.17 ms, because the
+// N = 64 / 128 layers are not L2-bound but shared-memory-operand-bound (a 128x64x16 MMA reads 6 KB of smem in its 32
+// tensor cycles = 192 B/cycle against the SM's 128 B/cycle) and the temporal boxes pad T = 13 to 16 (+23 % MMAs).
+static bool tr_wanted(const TrPlan& tr, double plain_cost) {
+  (void)plain_cost;
+  const char* v = getenv("MCG_TC_TR");
+  return v && atoi(v) != 0 && tr.ok;
 }
 
 bool tc_supported(const mcg_conv_geom* g) {
@@ -622,9 +885,33 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
     for (int kt = 0, j = 0; kt < g->kT; ++kt)
       for (int kh = 0; kh < g->kH; ++kh)
         for (int kw = 0; kw < g->kW; ++kw, ++j) P.taps[j] = TcTap{(int16_t)kw, (int16_t)kh, (int16_t)kt, (int16_t)j};
-    if ((rc = act_map(&ma, a, g->Cin, g->Wi, g->Hi, g->Ti, g->N, bx.w, bx.h, bx.t, bx.b, g->sW, g->sH, g->sT))) return rc;
     P.nboxes = P.nbw * P.nbh * P.nbt * P.nbb;
-    const TileCfg cfg = pick_tile(kFprop, P.nboxes, 1, g->Cout, taps * P.chunks);
+    double plain_cost = 0;
+    const TileCfg cfg = pick_tile(kFprop, P.nboxes, 1, g->Cout, taps * P.chunks, &plain_cost);
+    if (g->kT >= 2 && g->sT == 1 && !planar_chunk) {
+      const TrPlan tr = plan_tr(g->Wo, g->Ho, g->To, g->N, g->Cout, 1, g->kH * g->kW, P.chunks, g->kT);
+      if (tr_wanted(tr, plain_cost)) {
+        const Box tb = tr.bx;
+        P.BW = tb.w; P.BH = tb.h; P.BT = tb.t; P.BB = 1;
+        P.nbw = ceil_div(g->Wo, tb.w); P.nbh = ceil_div(g->Ho, tb.h); P.nbt = ceil_div(g->To, tb.t); P.nbb = g->N;
+        P.nboxes = P.nbw * P.nbh * P.nbt * P.nbb;
+        P.tr_kT = g->kT; P.tr_kstep = g->kH * g->kW; P.tr_rev = 0;
+        P.tr_frame_bytes = tb.w * tb.h * 128; P.tr_ablock_bytes = (tb.t + g->kT - 1) * P.tr_frame_bytes;
+        P.tr_aslots = tr.aslots; P.tr_bslots = tr.bslots;
+        P.tap_count[0] = g->kH * g->kW;
+        for (int kh = 0, j = 0; kh < g->kH; ++kh)
+          for (int kw = 0; kw < g->kW; ++kw, ++j) P.taps[j] = TcTap{(int16_t)kw, (int16_t)kh, 0, (int16_t)j};
+        if ((rc = act_map(&ma, a, g->Cin, g->Wi, g->Hi, g->Ti, g->N, tb.w, tb.h, tb.t + g->kT - 1, 1, g->sW, g->sH, 1))) return rc;
+        P.ntn = g->Cout / tr.bn;
+        P.ntiles = P.ntn;
+        const int grid = split_units(P, (long long)P.ntiles * P.nboxes, 1);
+        uint64_t d2[2] = {(uint64_t)P.Ktot, (uint64_t)wrows}, s2[1] = {(uint64_t)P.Ktot * 2};
+        uint32_t b2[2] = {64, (uint32_t)tr.bn}, e2[2] = {1, 1};
+        if ((rc = get_map(&mb, b, 2, d2, s2, b2, e2))) return rc;
+        return launch_tr_cfg<kFprop>(tr.bn, tr.mt, ma, mb, P, grid, out, bias, st, who);
+      }
+    }
+    if ((rc = act_map(&ma, a, g->Cin, g->Wi, g->Hi, g->Ti, g->N, bx.w, bx.h, bx.t, bx.b, g->sW, g->sH, g->sT))) return rc;
     P.ntn = g->Cout / cfg.bn;
     P.ntiles = P.ntn;
     const int grid = split_units(P, (long long)P.ntiles * P.nboxes, 1);
@@ -668,9 +955,45 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
       P.tap_count[c] = j - P.tap_begin[c];
       if (P.tap_count[c] > max_taps) max_taps = P.tap_count[c];
     }
-    if ((rc = act_map(&ma, a, g->Cout, g->Wo, g->Ho, g->To, g->N, bx.w, bx.h, bx.t, bx.b, 1, 1, 1))) return rc;
     P.nboxes = P.nbw * P.nbh * P.nbt * P.nbb;
-    const TileCfg cfg = pick_tile(kDgrad, P.nboxes, ncls, g->Cin, max_taps * P.chunks);
+    double plain_cost = 0;
+    const TileCfg cfg = pick_tile(kDgrad, P.nboxes, ncls, g->Cin, max_taps * P.chunks, &plain_cost);
+    if (g->kT >= 2 && g->sT == 1) {
+      const TrPlan tr = plan_tr(EW, EH, ET, g->N, g->Cin, ncls, max_taps / g->kT, P.chunks, g->kT);
+      if (tr_wanted(tr, plain_cost)) {
+        const Box tb = tr.bx;
+        P.BW = tb.w; P.BH = tb.h; P.BT = tb.t; P.BB = 1;
+        P.nbw = ceil_div(EW, tb.w); P.nbh = ceil_div(EH, tb.h); P.nbt = ceil_div(ET, tb.t); P.nbb = g->N;
+        P.nboxes = P.nbw * P.nbh * P.nbt * P.nbb;
+        P.tr_kT = g->kT; P.tr_kstep = g->kH * g->kW; P.tr_rev = 1;
+        P.tr_frame_bytes = tb.w * tb.h * 128; P.tr_ablock_bytes = (tb.t + g->kT - 1) * P.tr_frame_bytes;
+        P.tr_aslots = tr.aslots; P.tr_bslots = tr.bslots;
+        // groups: the (kh, kw) taps of each class; every kt belongs to it (ct = 1).  dy frame of tap kt = t + pT - kt.
+        int jg = 0;
+        for (int c = 0; c < ncls; ++c) {
+          const int pw = c % cw, ph = (c / cw) % ch;
+          P.tap_begin[c] = jg;
+          for (int kh = 0; kh < g->kH; ++kh) {
+            if ((ph + g->pH - kh) % ch) continue;
+            for (int kw = 0; kw < g->kW; ++kw) {
+              if ((pw + g->pW - kw) % cw) continue;
+              P.taps[jg++] = TcTap{(int16_t)((pw + g->pW - kw) / cw), (int16_t)((ph + g->pH - kh) / ch),
+                                   (int16_t)(g->pT - (g->kT - 1)), (int16_t)(kh * g->kW + kw)};
+            }
+          }
+          P.tap_count[c] = jg - P.tap_begin[c];
+        }
+        if ((rc = act_map(&ma, a, g->Cout, g->Wo, g->Ho, g->To, g->N, tb.w, tb.h, tb.t + g->kT - 1, 1, 1, 1, 1))) return rc;
+        P.ntn = g->Cin / tr.bn;
+        P.ntiles = ncls * P.ntn;
+        const int grid = split_units(P, (long long)P.ntiles * P.nboxes, 1);
+        uint64_t d2[2] = {(uint64_t)P.Ktot, (uint64_t)wrows}, s2[1] = {(uint64_t)P.Ktot * 2};
+        uint32_t b2[2] = {64, 64}, e2[2] = {1, 1};
+        if ((rc = get_map(&mb, b, 2, d2, s2, b2, e2))) return rc;
+        return launch_tr_cfg<kDgrad>(tr.bn, tr.mt, ma, mb, P, grid, out, bias, st, who);
+      }
+    }
+    if ((rc = act_map(&ma, a, g->Cout, g->Wo, g->Ho, g->To, g->N, bx.w, bx.h, bx.t, bx.b, 1, 1, 1))) return rc;
     P.ntn = g->Cin / cfg.bn;
     P.ntiles = ncls * P.ntn;
     const int grid = split_units(P, (long long)P.ntiles * P.nboxes, 1);

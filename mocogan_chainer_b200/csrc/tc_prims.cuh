@@ -185,6 +185,9 @@ __device__ __forceinline__ bool mbar_wait_a(uint32_t bar, uint32_t parity, int* 
   if (err_flag) atomicExch(err_flag, 1);
   return false;
 }
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }

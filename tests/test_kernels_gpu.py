@@ -155,6 +155,17 @@ def test_conv_tcgen05_every_tile_shape(K, mt, bn, monkeypatch):
         run_conv_case(K, case, K.IMPL_TC, torch.bfloat16, TOL_BF16)
 
 
+@pytest.mark.parametrize("r", [16, 32, 64])
+def test_conv_tcgen05_temporal_tap_reuse(K, r, monkeypatch):
+    """The opt-in temporal re-use kernel (MCG_TC_TR=1: one TMA box of BT + kT - 1 frames serves the kT temporal taps):
+    every frame-row count R on 3-D layers with remainders in T, H and W.  (Off by default: see tc_conv.cu / DESIGN.md.)"""
+    monkeypatch.setenv("MCG_TC_TR", "1")
+    monkeypatch.setenv("MCG_TC_TR_R", str(r))
+    for case in (("tr3d", 3, 3, 64, 128, (9, 12, 20), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
+                 ("tr3d_wide", 3, 2, 128, 256, (7, 16, 16), (4, 4, 4), (1, 2, 2), (0, 1, 1))):
+        run_conv_case(K, case, K.IMPL_TC, torch.bfloat16, TOL_BF16)
+
+
 def test_conv_tc_padded_weight_rows(K):
     """MCG_W_ROWS: the generator's first layer (60 = dim_zc + dim_zm channels, net.py:44) on tcgen05 — dy is zero-padded
     to 64 channels, the weight / dw keep 60 rows; compared with the oracle convolution that has Cout = 60."""
