@@ -47,5 +47,9 @@ class SerialIterator(object):
         return self.epoch + self.current_position / float(len(self.dataset))
 
     def serialize(self, serializer):
+        """SerialIterator.serialize of Chainer v3: current_position, epoch, is_new_epoch and the shuffled order."""
         serializer("current_position", (self, "current_position"))
         serializer("epoch", (self, "epoch"))
+        serializer("is_new_epoch", (self, "is_new_epoch"))
+        if self._order is not None:
+            serializer("order", (self, "_order"))

@@ -78,4 +78,23 @@ class Adam(Optimizer):
             apply()
 
     def serialize(self, serializer):
+        """GradientMethod.serialize of Chainer v3: `t`, `epoch`, then for every parameter its update rule's `t` and Adam
+        state `m`, `v` under `<param path>/` — arrays in Chainer's layouts (the flat moment buffers are sliced and
+        permuted exactly like Parameter.data)."""
+        if getattr(serializer, "is_saver", False) and self.t_dev is not None:
+            self.t = int(self.t_dev.item())   # a replayed CUDA graph advances only the device-side counter
         serializer("t", (self, "t"))
+        serializer("epoch", (self, "epoch"))
+        arena = self.target.arena()
+        off = 0
+        pad = lambda n: (n + 7) // 8 * 8
+        for path, p in self.target.namedparams():
+            sub = serializer[path]
+            sub("t", (self, "t"))
+            n = p.size
+            for key, buf in (("m", self.m), ("v", self.v)):
+                sub(key, p._to_logical(buf[off:off + n].view(p.internal_shape)))
+            off += pad(n)
+        assert off == arena.n
+        if self.t_dev is not None:   # the device-side step counter follows a load
+            self.t_dev.fill_(int(self.t))

@@ -39,7 +39,28 @@ class StandardUpdater(object):
         raise NotImplementedError
 
     def serialize(self, serializer):
+        """StandardUpdater.serialize of Chainer v3: iterators, then each optimizer and its target model, then the
+        iteration count — the `updater/...` part of a trainer snapshot (train.py:137-138)."""
+        for name, iterator in self._iterators.items():
+            if hasattr(iterator, "serialize"):
+                iterator.serialize(serializer["iterator:" + name])
+        for name, optimizer in self._optimizers.items():
+            optimizer.serialize(serializer["optimizer:" + name])
+            optimizer.target.serialize(serializer["model:" + name])
         serializer("iteration", (self, "iteration"))
+
+
+class TrainerState(object):
+    """What `extensions.snapshot()` writes for `training.Trainer` and `--resume` reads back (train.py:132-138,162-163),
+    restricted to the state that determines the continuation of training: everything under `updater/`.  (The
+    reference's trainer also stores LogReport / trigger bookkeeping under `extensions/`; that plumbing is out of
+    scope, so those keys are neither written nor required.)"""
+
+    def __init__(self, updater):
+        self.updater = updater
+
+    def serialize(self, serializer):
+        self.updater.serialize(serializer["updater"])
 
 
 def _to_device(x, device=None):

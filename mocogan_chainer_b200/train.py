@@ -117,9 +117,16 @@ def main(argv=None):
     save_path = Path('result') / args.save_name
     if rank == 0:
         save_path.mkdir(parents=True, exist_ok=True)
+    trainer_state = chainer.training.TrainerState(updater)
     if args.resume:
-        for name, m in (('image_gen', image_gen), ('image_dis', image_dis), ('video_dis', video_dis)):
-            chainer.serializers.load_npz(args.resume.format(name=name), m)
+        # train.py:162-163 `serializers.load_npz(args.resume, trainer)`: a full-trainer snapshot_epoch_N.npz restores the
+        # models, Adam moments and step counts, the iterator position / order and the iteration count.  (Additive: a
+        # pattern with {name} loads three per-model files instead.)
+        if '{name}' in args.resume:
+            for name, m in (('image_gen', image_gen), ('image_dis', image_dis), ('video_dis', video_dis)):
+                chainer.serializers.load_npz(args.resume.format(name=name), m)
+        else:
+            chainer.serializers.load_npz(args.resume, trainer_state)
     if rank == 0:
         print('[ Training configuration ]')
         print('# minibatch size: {}  max epoch: {}  data size: {}  model: {}  dtype: {}  world: {}'.format(
@@ -137,6 +144,7 @@ def main(argv=None):
                                              ls.get('VideoDiscriminator', float('nan')),
                                              updater.iteration / (time.time() - t0)))
             if ep % args.snapshot_interval == 0:
+                chainer.serializers.save_npz(save_path / 'snapshot_epoch_{}.npz'.format(ep), trainer_state)   # train.py:137
                 chainer.serializers.save_npz(save_path / 'image_gen_epoch_{}.npz'.format(ep), image_gen)
                 chainer.serializers.save_npz(save_path / 'image_dis_epoch_{}.npz'.format(ep), image_dis)
                 chainer.serializers.save_npz(save_path / 'video_dis_epoch_{}.npz'.format(ep), video_dis)

@@ -76,3 +76,39 @@ def test_graph_replay_equals_eager_with_same_seed():
     # wgrad uses fp32 atomics (order-dependent rounding), so compare to fp32 round-off amplified by 4 Adam steps
     assert (res[0] - res[1]).abs().max().item() < 5e-4
     assert (res[0] - res[1]).abs().mean().item() < 1e-5
+
+
+def test_trainer_snapshot_keys_and_resume(tmp_path, monkeypatch):
+    """§8f rank 2: `snapshot_epoch_N.npz` (extensions.snapshot, train.py:137-138) carries Chainer's trainer key schema
+    under `updater/` and `--resume` (train.py:162-163) restores models, Adam moments / step counts, the iterator and the
+    iteration count, so a resumed run continues where the first one stopped."""
+    from mocogan_chainer_b200 import train
+    monkeypatch.chdir(tmp_path)
+    common = ["-g", "0", "--synthetic", "8", "--batchsize", "4", "--snapshot_interval", "1", "--n_filters_gen", "8",
+              "--dtype", "fp32", "--seed", "3"]
+    up1 = train.main(common + ["--max_epoch", "2", "--save_name", "a"])
+    snap = tmp_path / "result" / "a" / "snapshot_epoch_1.npz"
+    with np.load(snap) as f:
+        keys = set(f.files)
+        for k in ("updater/iteration", "updater/iterator:main/current_position", "updater/iterator:main/epoch",
+                  "updater/iterator:main/is_new_epoch", "updater/iterator:main/order",
+                  "updater/model:image_gen/dc1/W", "updater/model:image_gen/g0/W_r/W", "updater/model:video_dis/bn2/avg_mean",
+                  "updater/optimizer:image_gen/t", "updater/optimizer:image_gen/epoch",
+                  "updater/optimizer:video_dis/dc4/W/m", "updater/optimizer:video_dis/dc4/W/v",
+                  "updater/optimizer:video_dis/dc4/W/t", "updater/optimizer:image_dis/bn3/gamma/m"):
+            assert k in keys, k
+        assert int(f["updater/iteration"]) == 2 and int(f["updater/optimizer:image_dis/t"]) == 2
+        assert f["updater/optimizer:video_dis/dc4/W/m"].shape == f["updater/model:video_dis/dc4/W"].shape == (64, 32, 4, 4, 4)
+        assert np.abs(f["updater/optimizer:video_dis/dc4/W/v"]).max() > 0
+        saved = {k: f[k].copy() for k in f.files}
+    # resume from epoch 1 and train to epoch 2: same iteration / step counts as the uninterrupted run
+    up2 = train.main(common + ["--max_epoch", "2", "--save_name", "b", "--resume", str(snap)])
+    assert up2.iteration == up1.iteration == 4 and up2.epoch == 2
+    for name in ("image_gen", "image_dis", "video_dis"):
+        assert up2.get_optimizer(name).t == 4 and int(up2.get_optimizer(name).t_dev.item()) == 4
+    # and loading alone reproduces the saved state bit for bit
+    from mocogan_chainer_b200 import chainer
+    chainer.serializers.load_npz(snap, chainer.training.TrainerState(up2))
+    again = chainer.serializers._collect(chainer.training.TrainerState(up2))
+    for k, v in saved.items():
+        assert np.array_equal(np.asarray(again[k]), v), k
