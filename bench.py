@@ -119,6 +119,18 @@ class PreStacked(list):
         return self.x.shape[0]
 
 
+def make_clip_cache(batch, seed, n_videos=70, frames=40):
+    """The e2e input: pre-decoded uint8 videos (MUG-shaped: 64x64x3, 40 frames each) in one pinned buffer; every step the
+    cache draws a 16-frame sub-sequence per clip (datasets.py:72-88), gathers the batch into pinned staging memory and the
+    updater copies it host->device as uint8; (v-128)/128 happens on the device (mocogan_chainer_b200/datasets.py)."""
+    from mocogan_chainer_b200.datasets import Uint8ClipCache
+    rng = np.random.default_rng(seed)
+    videos = [rng.integers(0, 256, size=(frames, 64, 64, 3), dtype=np.uint8) for _ in range(n_videos)]
+    labels = rng.integers(0, 6, size=n_videos)
+    np.random.seed(seed)
+    return Uint8ClipCache(videos, labels, batch, video_length=16, extract_speed=2, shuffle=True, pin=True)
+
+
 def build_updater(batch, seed, use_graph, model="normal"):
     import torch
     from mocogan_chainer_b200 import chainer, parallel
@@ -222,7 +234,8 @@ def gen_frames_per_s(torch, peaks, batch=256, video_len=32, iters=8):
         src.begin_step()
         return generate_samples.generate(G, batch, grid=True)
 
-    for _ in range(3):
+    torch.cuda.empty_cache()      # the training legs before this one leave multi-GB caches and graph pools behind
+    for _ in range(4):
         once()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -280,8 +293,13 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_dev = e0.elapsed_time(e1)
-    # ---- end to end through the public API: Updater.update() with pinned host batches, losses read back each step
-    for _ in range(2):
+    # ---- end to end through the public API: Updater.update() pulling uint8 clips from the pinned clip cache (iterator
+    # -> sub-sequence draw -> pinned staging batch -> H2D -> step), losses read back each step
+    cache = make_clip_cache(BATCH, parallel.shard_seed(1234, rank))
+    up._iterators["main"] = cache
+    up._static = up._stage = up._copy_stream = up._graph = None     # new input dtype/layout: re-stage and re-capture
+    up._eager_steps = 0
+    for _ in range(4):
         up.update()
     barrier()
     t0 = time.perf_counter()
@@ -327,8 +345,10 @@ def run_ours(args):
                    "l2": "no explicit flush: one step streams > 1 GB of activations/weights, >> 126 MB L2",
                    "weights": "random init (GlorotNormal/LeCunNormal)", "noise": "device Philox"},
         "clocks": clocks,
-        "e2e": {"value": e2e_steps_per_s, "unit": "steps/s", "h2d_bytes_per_step": int(it.x[0].numel() * 4 + it.t[0].numel() * 4),
-                "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e_steps_per_s, "unit": "steps/s",
+                "h2d_bytes_per_step": int(BATCH * 16 * 64 * 64 * 3 + BATCH * 4),
+                "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / args.steps,
+                "input": "uint8 clips from a pinned host cache, normalised on the device (datasets.py:72-104 restated)"},
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": {"bound": "tensor", "kernel": dominant["kernel"], "layer": dominant["layer"],
                      "achieved": dominant["tflops"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s",

@@ -25,7 +25,7 @@ extern "C" {
 #endif
 
 #define MCG_VERSION 100
-enum { MCG_F32 = 0, MCG_BF16 = 1 };
+enum { MCG_F32 = 0, MCG_BF16 = 1, MCG_U8 = 2 };   /* MCG_U8: only as the SOURCE of mcg_pack_video (pre-decoded pixels) */
 enum { MCG_ACT_NONE = 0, MCG_ACT_RELU = 1, MCG_ACT_LRELU = 2, MCG_ACT_TANH = 3 };
 enum { MCG_IMPL_SIMT = 0, MCG_IMPL_TC = 1 };          /* fp32 CUDA-core path | tcgen05 bf16 path */
 /* OR-ed into `impl` for fprop/wgrad of a layer with Cin <= 16: the workspace already holds this x's im2col matrix
@@ -97,7 +97,9 @@ int mcg_affine_act_noise(const void* y, long long M, int C, long long P, int dty
                          void* out, int out_dtype, void* stream);
 /* mcg_pack_video: gathers a video given by arbitrary element strides into channels-last (N,T',H,W,C) and adds
  *   noise as above: Variable x[:, :, t] / transpose / add_noise of updater.py:97-108 and net.py:148,189.
- *   If frame_ptr != NULL only frame *frame_ptr is taken (T' = 1), read on the device so graphs replay. */
+ *   If frame_ptr != NULL only frame *frame_ptr is taken (T' = 1), read on the device so graphs replay.
+ *   src_dtype MCG_U8: src holds pre-decoded pixels, read as (v - 128) / 128 (datasets.py:91) — the input pipeline's
+ *   normalisation fused into this pass. */
 int mcg_pack_video(const void* src, int src_dtype, int N, int C, int T, int H, int W, long long s_n,
                    long long s_c, long long s_t, long long s_h, long long s_w, const int* frame_ptr, float sigma,
                    const float* noise, long long ns_n, long long ns_c, long long ns_p, const void* rng_state,

@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmcg.so")
 
-F32, BF16 = 0, 1
+F32, BF16, U8 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 IMPL_SIMT, IMPL_TC = 0, 1
 

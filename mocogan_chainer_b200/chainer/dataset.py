@@ -15,7 +15,10 @@ class DatasetMixin(object):
 
 
 def concat_examples(batch, device=None, padding=None):
-    """list of (x, label) -> (stacked x, stacked labels); labels of None stay None (datasets.py:166)."""
+    """list of (x, label) -> (stacked x, stacked labels); labels of None stay None (datasets.py:166).  A batch object
+    that is already stacked (attributes x, t — the uint8 clip cache's) is handed through."""
+    if hasattr(batch, "x") and hasattr(batch, "t"):
+        return batch.x, batch.t
     first = batch[0]
     if isinstance(first, tuple):
         cols = []

@@ -44,6 +44,10 @@ template <> __device__ __forceinline__ float ld<float>(const float* p, long long
 template <> __device__ __forceinline__ float ld<__nv_bfloat16>(const __nv_bfloat16* p, long long i) {
   return __bfloat162float(p[i]);
 }
+// uint8 pixels are read already normalised: (v - 128) / 128, the reference's datasets.py:91 (input pipeline only)
+template <> __device__ __forceinline__ float ld<unsigned char>(const unsigned char* p, long long i) {
+  return ((float)p[i] - 128.f) / 128.f;
+}
 template <typename T> __device__ __forceinline__ void st(T* p, long long i, float v);
 template <> __device__ __forceinline__ void st<float>(float* p, long long i, float v) { p[i] = v; }
 template <> __device__ __forceinline__ void st<__nv_bfloat16>(__nv_bfloat16* p, long long i, float v) {

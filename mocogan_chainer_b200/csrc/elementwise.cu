@@ -629,9 +629,19 @@ int mcg_pack_video(const void* src, int src_dtype, int N, int C, int T, int H, i
                    int out_dtype, void* stream) {
   if (!src || !out || N <= 0 || C <= 0 || T <= 0 || H <= 0 || W <= 0)
     MCG_FAIL(MCG_ERR_SHAPE, "mcg_pack_video: bad arguments");
-  if (!dtype_ok(src_dtype) || !dtype_ok(out_dtype)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_pack_video: dtype");
+  if ((!dtype_ok(src_dtype) && src_dtype != MCG_U8) || !dtype_ok(out_dtype)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_pack_video: dtype");
   cudaStream_t st = as_stream(stream);
   long long total = (long long)N * (frame_ptr ? 1 : T) * H * W;
+  if (src_dtype == MCG_U8) {   // pre-decoded pixels: normalised (v - 128) / 128 as they are read (datasets.py:91)
+    dispatch1(out_dtype, [&](auto to) {
+      using TO = decltype(to);
+      pack_video_kernel<unsigned char, TO><<<grid_for(total), 256, 0, st>>>((const unsigned char*)src, N, C, T, H, W, s_n, s_c, s_t,
+                                                                          s_h, s_w, frame_ptr, sigma, noise, ns_n, ns_c, ns_p,
+                                                                          (const StepState*)rng_state, call_id, (TO*)out);
+    });
+    MCG_CHECK_LAUNCH("mcg_pack_video(u8)");
+    return 0;
+  }
   const bool plain = !frame_ptr && !noise && (sigma == 0.f || !rng_state);
   if (plain && C > 4) {   // pure layout / dtype conversion of a wide tensor
     dispatch2(src_dtype, out_dtype, [&](auto ti, auto to) {

@@ -8,7 +8,7 @@ import torch
 from . import _lib
 from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, BF16, F32, IMPL_SIMT, IMPL_TC, ConvGeom, check  # noqa: F401
 
-_DT = {torch.float32: F32, torch.bfloat16: BF16}
+_DT = {torch.float32: F32, torch.bfloat16: BF16, torch.uint8: _lib.U8}   # uint8 only as mcg_pack_video's source
 _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
 
 

@@ -186,7 +186,8 @@ class Updater(chainer.training.StandardUpdater):
         slot = self._stage[k]
         if slot is None:
             dev = torch.device("cuda", torch.cuda.current_device())
-            slot = self._stage[k] = {"x": torch.empty(x.shape, dtype=x.dtype, device=dev),
+            # same strides as the host batch (the uint8 clip cache hands out a channels-last view): a plain memcpy
+            slot = self._stage[k] = {"x": torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=dev),
                                      "t": None if t is None else torch.empty(t.shape, dtype=torch.int32, device=dev),
                                      "ready": torch.cuda.Event(), "consumed": None}
         cs = self._copy_stream
@@ -211,11 +212,13 @@ class Updater(chainer.training.StandardUpdater):
         main.wait_event(slot["ready"])
         self._flags = slot["flags"]
         self._stage_next = 1 - k
-        self._issue_h2d(1 - k, self._next_host_batch())      # overlaps with the step launched below
-        self.step_host_inputs(slot["x"], slot["t"])           # device->static copy + graph replay on `main`
+        self.step_host_inputs(slot["x"], slot["t"])           # device->static copy + graph replay on `main` (asynchronous)
         ev = torch.cuda.Event()
         ev.record(main)
         slot["consumed"] = ev
+        # the host assembles batch i+1 (sub-sequence draws, gather into pinned memory) and starts its H2D copy while the
+        # device runs step i
+        self._issue_h2d(1 - k, self._next_host_batch())
 
     def step_host_inputs(self, x_real, t_real):
         """CUDA-graph path: the batch (host or device) is copied straight into static device buffers, the device part
@@ -229,7 +232,7 @@ class Updater(chainer.training.StandardUpdater):
         t_real = None if t_real is None else as_t(t_real)
         if self._static is None:
             dev = torch.device("cuda", torch.cuda.current_device())
-            self._static = (torch.empty(x_real.shape, dtype=x_real.dtype, device=dev),
+            self._static = (torch.empty_strided(x_real.shape, x_real.stride(), dtype=x_real.dtype, device=dev),
                             None if t_real is None else torch.empty(t_real.shape, dtype=torch.int32, device=dev))
         sx, st = self._static
         sx.copy_(x_real, non_blocking=True)

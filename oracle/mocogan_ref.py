@@ -397,3 +397,27 @@ def to_grid(videos, size):
             if i * size + j < bs:
                 grid[:, :, i * h:i * h + h, j * w:j * w + w] = videos[:, i * size + j]
     return grid
+
+
+# ------------------------------------------------------------------------------------------------ input pipeline
+def subsequence_indices(video_len, video_length, extract_speed, randint):
+    """datasets.py:72-88 (MugDataset.get_example; MovingMnistDataset uses the `else` branch only, :141-147): which frames
+    of a stored video make up one training clip.  `randint(gap)` stands for `np.random.randint(0, gap, 1)[0]`.
+    Long videos (> video_length * extract_speed) are sampled every ~extract_speed-th frame (np.linspace with int32
+    truncation), shorter ones give a contiguous window."""
+    if video_len < video_length:
+        raise ValueError('invalid video length: {} < {}'.format(video_len, video_length))
+    if extract_speed and video_len > video_length * extract_speed:
+        needed = extract_speed * (video_length - 1)
+        gap = video_len - needed
+        start = 0 if gap == 0 else randint(gap)
+        return np.linspace(start, start + needed, video_length, endpoint=True, dtype=np.int32)
+    gap = video_len - video_length
+    start = 0 if gap == 0 else randint(gap)
+    return np.arange(start, start + video_length)
+
+
+def normalize_clip(frames_u8):
+    """datasets.py:91-104: frames (T, H, W, C) uint8 -> float32 clip (C, T, H, W) = (v - 128) / 128."""
+    video = (np.asarray(frames_u8, dtype=np.float32) - 128.) / 128.
+    return video.transpose(3, 0, 1, 2)

@@ -164,3 +164,34 @@ def test_oracle_to_grid_restates_util_py():
     assert g.shape == (2, 1, 4, 4)
     assert np.array_equal(g[:, :, 0:2, 2:4], u[:, 1]) and np.array_equal(g[:, :, 2:4, 0:2], u[:, 2])
     assert (g[:, :, 2:4, 2:4] == 0).all()          # the fourth cell has no video: black
+
+
+def test_uint8_clip_cache_follows_datasets_py():
+    """§8f rank 3: the clip cache draws sub-sequences exactly like datasets.py:72-88 (same np.random stream) and its
+    uint8 batch, normalised (v-128)/128, is the reference's float32 batch (datasets.py:91-104)."""
+    import numpy as np
+    from mocogan_chainer_b200.chainer.dataset import concat_examples
+    from mocogan_chainer_b200.datasets import Uint8ClipCache
+    from oracle import mocogan_ref as ref
+    rng = np.random.default_rng(0)
+    lens = [16, 20, 33, 40, 17]                      # 33 and 40 > 16 * 2: the extract_speed branch
+    videos = [rng.integers(0, 256, size=(n, 8, 8, 3), dtype=np.uint8) for n in lens]
+    labels = [0, 1, 2, 3, 4]
+    np.random.seed(7)
+    cache = Uint8ClipCache(videos, labels, batch_size=3, video_length=16, extract_speed=2, shuffle=True, pin=False)
+    order = cache._order.copy()
+    state = np.random.get_state()
+    x, t = concat_examples(cache.next())
+    assert tuple(x.shape) == (3, 3, 16, 8, 8) and x.dtype.is_floating_point is False
+    np.random.set_state(state)                       # replay the draws the cache made
+    for b, vid in enumerate(order[:3]):
+        idx = ref.subsequence_indices(lens[vid], 16, 2, lambda gap: np.random.randint(0, gap, 1)[0])
+        want = ref.normalize_clip(videos[vid][idx])                       # (C, T, H, W) float32
+        got = (x[b].numpy().astype(np.float32) - 128.) / 128.
+        assert np.array_equal(got, want) and int(t[b]) == labels[vid]
+    assert cache.epoch == 0 and not cache.is_new_epoch
+    cache.next()
+    assert cache.epoch == 1 and cache.is_new_epoch and cache.current_position == 1
+    # linspace branch really subsamples: frames two apart
+    idx = ref.subsequence_indices(40, 16, 2, lambda gap: 3)
+    assert idx[0] == 3 and idx[-1] == 33 and np.all(np.diff(idx) == 2)

@@ -112,3 +112,26 @@ def test_trainer_snapshot_keys_and_resume(tmp_path, monkeypatch):
     again = chainer.serializers._collect(chainer.training.TrainerState(up2))
     for k, v in saved.items():
         assert np.array_equal(np.asarray(again[k]), v), k
+
+
+def test_uint8_batch_equals_float_batch():
+    """A uint8 channels-last batch (the clip cache's) through the step == the same clips normalised on the host
+    (datasets.py:91) through the step: the (v-128)/128 fused into mcg_pack_video is exact."""
+    from mocogan_chainer_b200 import chainer
+    from mocogan_chainer_b200 import random as mrandom
+    from tests.test_step_gpu import build_pair
+    rng = np.random.default_rng(2)
+    u8 = rng.integers(0, 256, size=(2, 16, 64, 64, 3), dtype=np.uint8)               # (N, T, H, W, C)
+    xf = ((u8.astype(np.float32) - 128.) / 128.).transpose(0, 4, 1, 2, 3).copy()    # (N, C, T, H, W) float32
+    t = torch.tensor([1, 4], dtype=torch.int32, device="cuda")
+    losses = []
+    for x in (torch.from_numpy(u8).cuda().permute(0, 4, 1, 2, 3), torch.from_numpy(xf).cuda()):
+        np.random.seed(0)
+        chainer.config.compute_dtype = "fp32"
+        _, _, _, up, _ = build_pair("mug_normal", 8, "fp32")
+        mrandom.set_source(mrandom.DeviceRandom(seed=7, video_length=16))
+        up.step_on_device(x, t)
+        torch.cuda.synchronize()
+        losses.append({k: float(v) for k, v in up.losses.items()})
+    for k in losses[0]:
+        assert abs(losses[0][k] - losses[1][k]) < 1e-6, (k, losses)
