@@ -341,7 +341,8 @@ def run_ours(args):
         "config": {"workload": "BASELINE config 2: MoCoGAN normal model (train.py MUG wiring), clips (35,3,16,64,64) "
                                "per GPU, one update_core (G+Di+Dv) per step" + ("; data-parallel, NCCL all-reduce of the "
                                "three flat gradient buffers" if world > 1 else ""),
-                   "global_batch": BATCH * world, "parallelism": "dp%d" % world, "cuda_graph": up._graph is not None,
+                   "global_batch": BATCH * world, "parallelism": "dp%d" % world, "dp_overlap": parallel.describe() if world > 1 else None,
+                   "cuda_graph": up._graph is not None,
                    "l2": "no explicit flush: one step streams > 1 GB of activations/weights, >> 126 MB L2",
                    "weights": "random init (GlorotNormal/LeCunNormal)", "noise": "device Philox"},
         "clocks": clocks,

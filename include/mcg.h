@@ -174,6 +174,12 @@ int mcg_int_add(int* p, int delta, void* stream);   /* *p += delta on the stream
  * Synchronises the device; for tests and smoke(), never on the hot path.                                  */
 int mcg_tc_error_flag(int reset);
 
+/* SMs the persistent tcgen05 kernels may occupy (0 = all; default from MCG_TC_SMS).  Additive, no reference equivalent:
+ * the data-parallel layer reserves a few SMs for the CTAs of the all-reduce that overlaps backward, so a
+ * one-CTA-per-SM grid never runs a second wave behind them.  Not a per-launch argument: set once before the first step. */
+int mcg_set_tc_sm_limit(int sms);
+int mcg_get_tc_sm_limit(void);
+
 /* Number of kernels launched through this library since load (bench.py's gpu_launches).                   */
 long long mcg_launch_count(void);
 

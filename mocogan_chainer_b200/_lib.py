@@ -57,6 +57,8 @@ SIGNATURES = {
     "mcg_randint": (_i, [_p, _ll, _i, _p, _i, _p]),
     "mcg_int_add": (_i, [_p, _i, _p]),
     "mcg_tc_error_flag": (_i, [_i]),
+    "mcg_set_tc_sm_limit": (_i, [_i]),
+    "mcg_get_tc_sm_limit": (_i, []),
 }
 
 _lib = None

@@ -242,6 +242,7 @@ class Parameter(Variable):
         self.cl = bool(channels_last_weight and self._init_array.ndim >= 3)
         self._store = self._gstore = self._bstore = None
         self.update_rule = None
+        self.grad_written_hook = None   # data-parallel layer: called after a kernel accumulated into this .grad
 
     @property
     def internal_shape(self):
@@ -375,6 +376,7 @@ class ParamArena(object):
             offs.append(tot)
             tot += pad(n)
         self.n = tot
+        self.offsets = {id(p): (o, n) for p, o, n in zip(self.params, offs, sizes)}   # slice of each parameter
         # 128-byte aligned tails for TMA: pad whole arena
         self.data = torch.zeros(tot, dtype=torch.float32, device=device)
         self.grad = torch.zeros(tot, dtype=torch.float32, device=device)

@@ -195,6 +195,8 @@ class ConvolutionND(FunctionNode):
                 K.conv_wgrad(g, self.xp, gyp, W.gstore, self.impl, ws=self.cols_ws, cols_valid=self.cols_ws is not None)
             else:
                 K.conv_wgrad(g, gyp, self.xp, W.gstore, self.impl | wr, ws=ws, cols_valid=ws is not None)
+            if W.grad_written_hook is not None:
+                W.grad_written_hook(W)
         self.cols_ws = None
         if 2 in idx and b is not None and self.bias_grad:
             gb_src = as_physical(gys[0])  # original precision: the fp32 loss gradient of the last layer cancels heavily

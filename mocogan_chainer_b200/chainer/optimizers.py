@@ -18,6 +18,7 @@ class Adam(Optimizer):
         # weights next must be ordered after it; the Updater puts the video discriminator's update on the stream of the
         # only branch that needs it before the end of the step.
         self.update_stream = None
+        self.grad_buckets = None     # data-parallel layer: early all-reduce of the large weight gradients
 
     def setup(self, link):
         super(Adam, self).setup(link)
@@ -40,6 +41,8 @@ class Adam(Optimizer):
         if lossfun is not None:
             loss = lossfun(*args, **kwds)
             self.target.cleargrads()
+            if self.grad_buckets is not None:
+                self.grad_buckets.begin()
             marked = []
             for v in self.stop_variables:
                 if not v.stop:

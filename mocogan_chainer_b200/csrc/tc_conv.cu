@@ -15,6 +15,7 @@
 // boxes for fprop/dgrad, K steps for wgrad), so the load imbalance is at most one unit.
 #include "common.cuh"
 #include "tc_prims.cuh"
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -667,9 +668,22 @@ static int tc_env_int(const char* name) {
   const char* v = getenv(name);
   return v ? atoi(v) : 0;
 }
+// SMs the persistent kernels may occupy.  A data-parallel job leaves a few SMs to the collective's CTAs: a persistent
+// grid of one CTA per SM launched while k SMs are held by an all-reduce runs its last k CTAs as a second wave (up to 2x
+// the kernel time), a grid of sms - k CTAs does not (mcg_set_tc_sm_limit; 0 = all, MCG_TC_SMS overrides the default).
+static std::atomic<int> g_tc_sm_limit{-1};
+static int tc_sms() {
+  int lim = g_tc_sm_limit.load(std::memory_order_relaxed);
+  if (lim < 0) {
+    lim = tc_env_int("MCG_TC_SMS");
+    g_tc_sm_limit.store(lim, std::memory_order_relaxed);
+  }
+  const int n = num_sms();
+  return (lim > 0 && lim < n) ? lim : n;
+}
 static double step_cycles(int mt, int bn, long long active_ctas) {
   const double chip_bw = 7400.0, sm_cap = 110.0;   // L2 -> SM bytes per cycle: whole chip (measured on these kernels), one SM
-  const int sms = num_sms();
+  const int sms = tc_sms();
   double share = chip_bw / (double)(active_ctas < sms ? (active_ctas > 0 ? active_ctas : 1) : sms);
   if (share > sm_cap) share = sm_cap;
   const double bytes = mt * 16384.0 + bn * 128.0, mma = 2.0 * mt * bn;
@@ -678,7 +692,7 @@ static double step_cycles(int mt, int bn, long long active_ctas) {
 }
 static TileCfg pick_tile(int mode, long long nboxes, int ncls, int cols, int nk, double* cost_out = nullptr) {
   const int fm = tc_env_int("MCG_TC_MT"), fb = tc_env_int("MCG_TC_BN");
-  const int sms = num_sms();
+  const int sms = tc_sms();
   TileCfg best{1, 64};
   double best_cost = 1e300;
   const int bns[4] = {256, 192, 128, 64};
@@ -704,7 +718,7 @@ static TileCfg pick_tile(int mode, long long nboxes, int ncls, int cols, int nk,
 }
 // cut `units` into equal contiguous ranges, one per CTA
 static int split_units(TcParams& P, long long units, long long min_per_cta) {
-  const int sms = num_sms();
+  const int sms = tc_sms();
   long long ctas = units / (min_per_cta > 0 ? min_per_cta : 1);
   if (ctas > sms) ctas = sms;
   if (ctas < 1) ctas = 1;
@@ -757,7 +771,7 @@ static TrPlan plan_tr(int EW, int EH, int ET, int N, int cols, int ncls, int gro
   TrPlan best;
   best.ok = false;
   best.cost = 1e300;
-  const int sms = num_sms();
+  const int sms = tc_sms();
   const double chip_bw = 7400.0, sm_cap = 110.0;
   const int fm = tc_env_int("MCG_TC_MT"), fb = tc_env_int("MCG_TC_BN"), fr = tc_env_int("MCG_TC_TR_R");
   for (int bw = 1; bw <= 64; bw *= 2)
@@ -1440,6 +1454,13 @@ int mcg_conv_wgrad(const mcg_conv_geom* g, const void* x, const void* dy, float*
   }
   return simt_conv(2, g, dy, x, nullptr, nullptr, dw, dtype, MCG_F32, 1, as_stream(stream));
 }
+
+int mcg_set_tc_sm_limit(int sms) {
+  if (sms < 0) MCG_FAIL(MCG_ERR_SHAPE, "mcg_set_tc_sm_limit: %d < 0", sms);
+  g_tc_sm_limit.store(sms, std::memory_order_relaxed);
+  return 0;
+}
+int mcg_get_tc_sm_limit(void) { return tc_sms(); }
 
 int mcg_tc_error_flag(int reset) {
   int v = 0;

@@ -248,3 +248,12 @@ def tc_error_flag(reset=True):
 
 def launch_count():
     return lib().mcg_launch_count()
+
+
+def set_tc_sm_limit(sms):
+    """SMs the persistent tcgen05 kernels may occupy (0 = all): the data-parallel layer leaves a few to NCCL's CTAs."""
+    check(lib().mcg_set_tc_sm_limit(int(sms)), "mcg_set_tc_sm_limit")
+
+
+def get_tc_sm_limit():
+    return lib().mcg_get_tc_sm_limit()

@@ -13,6 +13,11 @@ import torch
 import torch.distributed as dist
 
 
+# defaults of the overlap knobs (see attach); chosen from the 2- and 8-GPU sweeps recorded in profiles/
+DEFAULT_BUCKETS = 0
+DEFAULT_THIN_CTAS = 0
+
+
 def init_from_env(backend=None):
     """Initialises the default process group from RANK / WORLD_SIZE / MASTER_* (torchrun).  Returns (rank, world)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -45,17 +50,128 @@ def broadcast_(flat, src=0, group=None):
     return flat
 
 
+class GradBuckets(object):
+    """All-reduce overlapped with backward (north_star).  The weight gradient of a discriminator's widest
+    layer is the first to be complete and most of the payload (Dv.dc4.W: 33.5 of 44.2 MB), so every LARGE parameter is
+    all-reduced on a communication stream as soon as the last kernel that accumulates into it has been launched, under
+    the rest of the backward pass; what is left (the small parameters, as the contiguous gaps of the flat gradient
+    buffer) is reduced when backward is over.  How many kernels write a parameter in one pass (2 for the
+    discriminators: real and fake chain; 1 for the generator) is LEARNED in the first pass, which uses the plain flat
+    all-reduce — identically on every rank, so all ranks issue the same collectives in the same order."""
+
+    def __init__(self, opt, group=None, min_numel=1 << 20, early_group=None):
+        self.group = group                                   # what is left when backward is over (exposed: full width)
+        self.early_group = early_group if early_group is not None else group   # under backward (may be a thin one)
+        self.arena = opt.target.arena()
+        self.big = {}
+        for p in self.arena.params:
+            off, n = self.arena.offsets[id(p)]
+            if n >= min_numel:
+                self.big[id(p)] = (off, n)
+                p.grad_written_hook = self.written
+        self.expected = None
+        self.comm = torch.cuda.Stream()
+        self.begin()
+
+    def begin(self):
+        self.count = {k: 0 for k in self.big}
+        self.events = {k: [] for k in self.big}
+        self.reduced = []
+
+    def written(self, p):
+        k = id(p)
+        if k not in self.big:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.events[k].append(ev)
+        self.count[k] += 1
+        if self.expected is not None and self.count[k] == self.expected.get(k, -1):
+            off, n = self.big[k]
+            for e in self.events[k]:
+                self.comm.wait_event(e)
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(self.arena.grad[off:off + n], op=dist.ReduceOp.SUM, group=self.early_group)
+            self.reduced.append((off, n))
+
+    def finish(self, flat):
+        """The optimizer's grad_transform: everything not reduced early, then wait for the communication stream."""
+        if self.expected is None:
+            self.expected = dict(self.count)       # first pass: learn the writer counts, reduce the whole buffer at once
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            return flat
+        pos = 0
+        for off, n in sorted(self.reduced):
+            if off > pos:
+                dist.all_reduce(flat[pos:off], op=dist.ReduceOp.SUM, group=self.group)
+            pos = off + n
+        if pos < flat.numel():
+            dist.all_reduce(flat[pos:], op=dist.ReduceOp.SUM, group=self.group)
+        torch.cuda.current_stream().wait_stream(self.comm)
+        return flat
+
+
+def _env_int(name, default):
+    v = os.environ.get(name, "")
+    return int(v) if v.strip() else default
+
+
+_thin_groups = {}
+
+
+def thin_group(max_ctas):
+    """A second NCCL communicator over all ranks whose kernels use at most `max_ctas` CTAs: for the all-reduces that run
+    UNDER backward.  The persistent tcgen05 kernels own whole SMs, so a wide collective launched beside them either waits
+    for SMs or pushes CTAs of the next convolution into a second wave; a thin one on SMs the convolutions leave free
+    (kernels.set_tc_sm_limit) does neither, and has the rest of the pass to finish in."""
+    if max_ctas not in _thin_groups:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.min_ctas = 1
+        opts.config.max_ctas = int(max_ctas)
+        _thin_groups[max_ctas] = dist.new_group(backend="nccl", pg_options=opts)
+    return _thin_groups[max_ctas]
+
+
 def attach(optimizers, group=None):
-    """Makes each Adam optimizer data-parallel: replicas start from rank 0's weights, gradients are averaged."""
+    """Makes each Adam optimizer data-parallel: replicas start from rank 0's weights, gradients are averaged.
+
+    On GPUs the knobs of the overlap (all read once, here; identical on every rank):
+      MCG_DP_BUCKETS=1      large weight gradients are all-reduced under the rest of backward (GradBuckets)
+      MCG_DP_THIN_CTAS=k    collectives that overlap backward go through a k-CTA communicator (0: the default one)
+      MCG_DP_SM_RESERVE=k   SMs the persistent convolution kernels leave free for them (default: MCG_DP_THIN_CTAS)
+    """
     w = dist.get_world_size(group) if dist.is_initialized() else 1
+    on_gpu = w > 1 and torch.cuda.is_available() and dist.get_backend(group) == "nccl"
+    buckets = on_gpu and _env_int("MCG_DP_BUCKETS", DEFAULT_BUCKETS) != 0
+    thin_ctas = _env_int("MCG_DP_THIN_CTAS", DEFAULT_THIN_CTAS) if on_gpu else 0
+    reserve = _env_int("MCG_DP_SM_RESERVE", thin_ctas) if on_gpu else 0
+    early = thin_group(thin_ctas) if thin_ctas > 0 and group is None else group
+    if on_gpu and reserve > 0:
+        from . import kernels as K
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        K.set_tc_sm_limit(max(sms - reserve, 1))
     for opt in optimizers:
         arena = opt.target.arena()
         broadcast_(arena.data, 0, group)
         arena.refresh_bf16()
         if w > 1:
-            opt.grad_transform = lambda g, _grp=group: allreduce_mean_(g, _grp)
+            # the image discriminator's all-reduce (after pass A) runs under all of pass B: overlapped as a whole
+            flat_group = early if type(opt.target).__name__ == "ImageDiscriminator" else group
+            opt.grad_transform = lambda g, _grp=flat_group: allreduce_mean_(g, _grp)
             opt.grad_scale = 1.0 / w
+            if buckets and hasattr(arena, "offsets") and arena.data.is_cuda and flat_group is group:
+                opt.grad_buckets = GradBuckets(opt, group, early_group=early)
+                if opt.grad_buckets.big:
+                    opt.grad_transform = opt.grad_buckets.finish
+                else:
+                    opt.grad_buckets = None
     return w
+
+
+def describe():
+    """The data-parallel configuration in force, for bench.py's `config`."""
+    return {"buckets": _env_int("MCG_DP_BUCKETS", DEFAULT_BUCKETS), "thin_ctas": _env_int("MCG_DP_THIN_CTAS", DEFAULT_THIN_CTAS),
+            "sm_reserve": _env_int("MCG_DP_SM_RESERVE", _env_int("MCG_DP_THIN_CTAS", DEFAULT_THIN_CTAS))}
 
 
 def shard_seed(base_seed, rank):
