@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcg.so")
+LIB_PATH = os.environ.get("MCG_LIB") or os.path.join(_HERE, "libmcg.so")   # MCG_LIB: A/B builds of the same ABI
 
 F32, BF16, U8 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3

@@ -106,6 +106,51 @@ def pack_video(x, frame=None, noise=None):
     return PackVideo(frame, noise).apply((x,))[0]
 
 
+class ConcatLabelVideo(FunctionNode):
+    """Updater.concat_label_video (updater.py:65-76, cgan): `dim_zl` planes of -1 with +1 at each clip's label plane,
+    F.concat'ed to the clip on the channel axis.  Output storage is channels-last (N,T,H,W,C+dim_zl), so the
+    discriminators' input pass reads it like any clip; backward hands the clip channels' slice of the (lazy) video
+    gradient on to the generator (F.concat's backward, updater.py:104-106) — the label planes are constants.
+    Layout plumbing only (torch copies, no arithmetic): cgan is not one of BASELINE.json's measured configurations."""
+
+    def __init__(self, label, dim_zl):
+        super(ConcatLabelVideo, self).__init__()
+        self.label, self.dim_zl = label, int(dim_zl)
+
+    def forward(self, inputs):
+        x, = inputs
+        if x.dim() != 5:
+            raise ValueError("concat_label_video expects (N,C,T,H,W), got %s" % (tuple(x.shape),))
+        p = physical_view(x)
+        N, T, H, W, Cc = p.shape
+        self.C = Cc
+        odt = torch.float32 if x.dtype == torch.uint8 else x.dtype
+        out = torch.empty((N, T, H, W, Cc + self.dim_zl), dtype=odt, device=x.device)
+        if x.dtype == torch.uint8:   # clips from the uint8 cache: datasets.py:91's (v - 128) / 128
+            out[..., :Cc].copy_((p.float() - 128.0) / 128.0)
+        else:
+            out[..., :Cc].copy_(p)
+        lab = self.label.to(device=x.device, dtype=torch.int64)
+        planes = torch.where(lab[:, None] == torch.arange(self.dim_zl, device=x.device)[None, :], 1.0, -1.0).to(odt)
+        out[..., Cc:] = planes[:, None, None, None, :]
+        return logical_view(out, 3),
+
+    def backward(self, idx, gys):
+        g = gys[0]
+        Cc = self.C
+        if isinstance(g, VideoGrad):
+            cut = lambda a: None if a is None else a[..., :Cc].contiguous()
+            return VideoGrad(cut(g.gv), cut(g.gi), g.frame_ptr, g.ops),
+        return g[:, :Cc],
+
+
+def concat_label_video(video, label, dim_zl):
+    lab = label.data if isinstance(label, Variable) else label
+    if not isinstance(video, Variable):
+        video = Variable(video, requires_grad=False)
+    return ConcatLabelVideo(lab, dim_zl).apply((video,))[0]
+
+
 # ---------------------------------------------------------------------------------------------- convolutions
 class ConvolutionND(FunctionNode):
     """F.convolution_2d / F.convolution_nd (net.py:149-156,190-197) when deconv=False;

@@ -27,6 +27,58 @@ extern std::atomic<long long> g_launches;
   } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// A step is ~270 short kernels in dependency chains, so the gap between a kernel's last CTA and the first CTA of the
+// next one is paid ~150 times on the critical path.  With MCG_PDL=1 every kernel of this library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel of the stream may be scheduled while its
+// predecessor drains, runs its prologue (barrier init, TMEM allocation, descriptor prefetch, index set-up), and blocks in
+// pdl_wait() — EVERY kernel's first action before touching global memory — until the predecessor has completed and its
+// writes are visible.  Because every kernel waits, completion stays transitive along a stream; kernels of other
+// libraries (torch, NCCL) in between are launched normally and act as full barriers.  The persistent tcgen05 kernels
+// additionally call pdl_launch_dependents() on entry (they own their SM for their whole life, so an early-scheduled
+// successor only occupies spare thread slots); without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifndef MCG_PDL_DEFAULT
+#define MCG_PDL_DEFAULT 0
+#endif
+// Streaming kernels: wait on entry.  MCG_PDL_EW_TRIGGER=1 (build flag) also lets THEIR successor be scheduled early; it
+// is off by default because an early-scheduled persistent convolution camps on the SM's shared memory while it waits
+// and keeps the other streams' convolutions out (branch concurrency).
+#ifndef MCG_PDL_EW_TRIGGER
+#define MCG_PDL_EW_TRIGGER 0
+#endif
+__device__ __forceinline__ void pdl_enter() {
+#if MCG_PDL_EW_TRIGGER
+  pdl_launch_dependents();
+#endif
+  pdl_wait();
+}
+int pdl_level();   // MCG_PDL (default MCG_PDL_DEFAULT), read once (elementwise.cu)
+
+template <typename... KArgs>
+struct PdlLaunch {
+  void (*kern)(KArgs...);
+  dim3 grid, block;
+  size_t smem;
+  cudaStream_t st;
+  template <typename... Args>
+  void operator()(Args&&... args) const {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_level() > 0 ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);   // errors surface in MCG_CHECK_LAUNCH
+  }
+};
+template <typename... KArgs>
+static inline PdlLaunch<KArgs...> pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  return PdlLaunch<KArgs...>{kern, grid, block, smem, st};
+}
 static inline int num_sms() {
   static int n = 0;
   if (!n) {

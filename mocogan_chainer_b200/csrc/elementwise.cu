@@ -6,6 +6,14 @@
 
 namespace mcg {
 
+int pdl_level() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCG_PDL");
+    v = e ? atoi(e) : MCG_PDL_DEFAULT;
+  }
+  return v;
+}
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -90,6 +98,7 @@ struct BnBwdF {  // sum g', sum g'*xhat with g' = g * act'(scale*y+shift)
 template <typename T, int VEC, typename F>
 __global__ void __launch_bounds__(kRedThreads) colreduce_kernel(F f, const T* p0, const T* p1, long long M, int C,
                                                                int tpr, float* __restrict__ partial) {
+  pdl_enter();
   extern __shared__ float red[];  // [rpb][tpr][2*VEC]
   const int CG = C / VEC;
   const int rpb = kRedThreads / tpr;
@@ -145,7 +154,7 @@ static int launch_colreduce(F f, const void* p0, const void* p1, long long M, in
     MCG_FAIL(MCG_ERR_WORKSPACE, "%s: workspace %zu < %zu", name, ws_bytes, (size_t)nblk * 2 * C * sizeof(float));
   size_t smem = (size_t)kRedThreads * 2 * VEC * sizeof(float);
   float* part = reinterpret_cast<float*>(ws);
-#define LAUNCH(T, V) colreduce_kernel<T, V, F><<<nblk, kRedThreads, smem, st>>>(f, (const T*)p0, (const T*)p1, M, C, tpr, part)
+#define LAUNCH(T, V) pdl(colreduce_kernel<T, V, F>, nblk, kRedThreads, smem, st)(f, (const T*)p0, (const T*)p1, M, C, tpr, part)
   if (dtype == MCG_F32) { if (VEC == 8) LAUNCH(float, 8); else LAUNCH(float, 1); }
   else if (dtype == MCG_BF16) { if (VEC == 8) LAUNCH(__nv_bfloat16, 8); else LAUNCH(__nv_bfloat16, 1); }
   else MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: dtype %d", name, dtype);
@@ -181,6 +190,7 @@ __global__ void __launch_bounds__(256) bn_stats_finalize(const float* partial, i
                                                          const float* gamma, const float* beta, float eps, float decay,
                                                          float* mean, float* invstd, float* scale, float* shift,
                                                          float* avg_mean, float* avg_var) {
+  pdl_enter();
   int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   double s, q;
@@ -204,6 +214,7 @@ __global__ void __launch_bounds__(256) bn_stats_finalize(const float* partial, i
 }
 __global__ void __launch_bounds__(256) sum2_finalize(const float* partial, int nblk, int C, float* out_a, float* out_b,
                                                      int accumulate, float* acc_a = nullptr, float* acc_b = nullptr) {
+  pdl_enter();
   int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   double s, q;
@@ -228,6 +239,7 @@ __global__ void __launch_bounds__(256) affine_act_noise_kernel(
     const float* __restrict__ shift, int act, float slope, float sigma, const float* __restrict__ noise,
     long long ns_n, long long ns_c, long long ns_p, const StepState* __restrict__ rng, int call_id,
     TO* __restrict__ out) {
+  pdl_enter();
   const int CG = C / VEC;
   const long long total = M * CG;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -282,6 +294,7 @@ __global__ void __launch_bounds__(256) pack_video_kernel(
     long long s_h, long long s_w, const int* __restrict__ frame_ptr, float sigma, const float* __restrict__ noise,
     long long ns_n, long long ns_c, long long ns_p, const StepState* __restrict__ rng, int call_id,
     TO* __restrict__ out) {
+  pdl_enter();
   // one thread per pixel: for a channels-first source the reads of each channel are coalesced along w and the C
   // outputs of a pixel are adjacent, so a warp writes one contiguous span
   const int Tout = frame_ptr ? 1 : T;
@@ -318,6 +331,7 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) pack_elem_kernel(const TI* __restrict__ src, int N, int C, int T, int H, int W,
                                                         long long s_n, long long s_c, long long s_t, long long s_h,
                                                         long long s_w, TO* __restrict__ out) {
+  pdl_enter();
   const long long total = (long long)N * T * H * W * C;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -343,6 +357,7 @@ __global__ void __launch_bounds__(256) act_bn_bwd_apply_kernel(
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ scale,
     const float* __restrict__ shift, int act, float slope, int use_output, const float* __restrict__ dgamma,
     const float* __restrict__ dbeta, float inv_m, TO* __restrict__ gy) {
+  pdl_enter();
   const int CG = C / VEC;
   const long long total = M * CG;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -400,6 +415,7 @@ __global__ void __launch_bounds__(256) tanh_bwd_video_kernel(const TG* __restric
                                                              const TO* __restrict__ out_tn, int N, int T, int HW,
                                                              int C, const int* __restrict__ frame_ptr,
                                                              TD* __restrict__ g_tn) {
+  pdl_enter();
   const int ft = frame_ptr ? *frame_ptr : -1;
   const long long per = (long long)HW * C;
   const long long total = (long long)T * N * per;
@@ -423,6 +439,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) video_to_uint8_kernel(const T* __restrict__ v, int Tn, int N, int C, int H, int W,
                                                              unsigned char* __restrict__ u8, unsigned char* __restrict__ grid,
                                                              int size) {
+  pdl_enter();
   // one thread per 4 consecutive w of one (t, n, c, h) row: four strided reads, one 32-bit store per output
   const int W4 = W / 4;   // launcher guarantees W % 4 == 0
   const long long total = (long long)Tn * N * C * H * W4;
@@ -457,6 +474,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    __nv_bfloat16* __restrict__ pb, long long n, float alpha,
                                                    float beta1, float beta2, float eps, float wd, float gscale,
                                                    const int* __restrict__ t_ptr) {
+  pdl_enter();
   __shared__ float lr_s;
   if (threadIdx.x == 0) {
     double t = (double)(*t_ptr);
@@ -479,20 +497,24 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 __global__ void cast_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     d[i] = __float2bfloat16_rn(s[i]);
 }
 __global__ void state_init_kernel(StepState* s, unsigned long long seed) {
+  pdl_enter();
   s->seed_lo = (uint32_t)seed; s->seed_hi = (uint32_t)(seed >> 32);
   s->step = 0; s->frame_t = 0; s->adam_t = 0; s->r0 = s->r1 = s->r2 = 0;
 }
 __global__ void state_advance_kernel(StepState* s, int T) {
+  pdl_enter();
   s->step += 1;
   s->adam_t += 1;
   uint4 r = philox4x32(make_uint4(0, 0, 0x7fffffff, s->step), make_uint2(s->seed_lo, s->seed_hi));
   s->frame_t = T > 0 ? r.x % (uint32_t)T : 0;
 }
 __global__ void randn_kernel(float* out, long long n, float sigma, const StepState* rng, int call_id) {
+  pdl_enter();
   long long n4 = (n + 3) / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float z[4];
@@ -502,6 +524,7 @@ __global__ void randn_kernel(float* out, long long n, float sigma, const StepSta
   }
 }
 __global__ void randint_kernel(int* out, long long n, int high, const StepState* rng, int call_id) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     uint4 r = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)call_id, rng->step),
                          make_uint2(rng->seed_lo, rng->seed_hi));
@@ -551,7 +574,7 @@ int mcg_bn_stats(const void* y, long long M, int C, int dtype, const float* gamm
   int rc = launch_colreduce(StatsF{}, y, nullptr, M, C, dtype, workspace, workspace_bytes, as_stream(stream), &nblk,
                             "mcg_bn_stats");
   if (rc) return rc;
-  bn_stats_finalize<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>((const float*)workspace, nblk, C, (double)M, gamma,
+  pdl(bn_stats_finalize, (C + 7) / 8, 256, 0, as_stream(stream))((const float*)workspace, nblk, C, (double)M, gamma,
                                                                     beta, eps, decay, mean, invstd, scale, shift,
                                                                     avg_mean, avg_var);
   MCG_CHECK_LAUNCH("mcg_bn_stats(finalize)");
@@ -565,8 +588,8 @@ int mcg_colsum(const void* g, long long M, int C, int dtype, float* out, int acc
   int rc = launch_colreduce(SumF{}, g, nullptr, M, C, dtype, workspace, workspace_bytes, as_stream(stream), &nblk,
                             "mcg_colsum");
   if (rc) return rc;
-  sum2_finalize<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>((const float*)workspace, nblk, C, out, nullptr,
-                                                                accumulate);
+  pdl(sum2_finalize, (C + 7) / 8, 256, 0, as_stream(stream))((const float*)workspace, nblk, C, out, nullptr,
+                                                                accumulate, nullptr, nullptr);
   MCG_CHECK_LAUNCH("mcg_colsum(finalize)");
   return 0;
 }
@@ -584,7 +607,7 @@ int mcg_act_bn_bwd_reduce(const void* g, const void* y, long long M, int C, int 
   if (rc) return rc;
   // partial[.,0,:] = sum g' -> dbeta ; partial[.,1,:] = sum g' xhat -> dgamma; acc_* are the parameter
   // gradients, which accumulate across the real and fake calls of one pass as in Chainer.
-  sum2_finalize<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>((const float*)workspace, nblk, C, dbeta, dgamma, 0,
+  pdl(sum2_finalize, (C + 7) / 8, 256, 0, as_stream(stream))((const float*)workspace, nblk, C, dbeta, dgamma, 0,
                                                                 acc_dbeta, acc_dgamma);
   MCG_CHECK_LAUNCH("mcg_act_bn_bwd_reduce(finalize)");
   return 0;
@@ -610,13 +633,13 @@ int mcg_affine_act_noise(const void* y, long long M, int C, long long P, int dty
     using TI = decltype(ti);
     using TO = decltype(to);
     if (C % 8 == 0 && 256 % (C / 8) == 0)   // a thread keeps its channel group: per-channel constants in registers
-      affine_act_noise_kernel<TI, TO, 8, true><<<grid_for(M * (C / 8)), 256, 0, st>>>(
+      pdl(affine_act_noise_kernel<TI, TO, 8, true>, grid_for(M * (C / 8)), 256, 0, st)(
           (const TI*)y, M, C, P, scale, shift, act, slope, sigma, noise, ns_n, ns_c, ns_p, rng, call_id, (TO*)out);
     else if (C % 8 == 0)
-      affine_act_noise_kernel<TI, TO, 8, false><<<grid_for(M * (C / 8)), 256, 0, st>>>(
+      pdl(affine_act_noise_kernel<TI, TO, 8, false>, grid_for(M * (C / 8)), 256, 0, st)(
           (const TI*)y, M, C, P, scale, shift, act, slope, sigma, noise, ns_n, ns_c, ns_p, rng, call_id, (TO*)out);
     else
-      affine_act_noise_kernel<TI, TO, 1, false><<<grid_for(M * C), 256, 0, st>>>(
+      pdl(affine_act_noise_kernel<TI, TO, 1, false>, grid_for(M * C), 256, 0, st)(
           (const TI*)y, M, C, P, scale, shift, act, slope, sigma, noise, ns_n, ns_c, ns_p, rng, call_id, (TO*)out);
   });
   MCG_CHECK_LAUNCH("mcg_affine_act_noise");
@@ -635,7 +658,7 @@ int mcg_pack_video(const void* src, int src_dtype, int N, int C, int T, int H, i
   if (src_dtype == MCG_U8) {   // pre-decoded pixels: normalised (v - 128) / 128 as they are read (datasets.py:91)
     dispatch1(out_dtype, [&](auto to) {
       using TO = decltype(to);
-      pack_video_kernel<unsigned char, TO><<<grid_for(total), 256, 0, st>>>((const unsigned char*)src, N, C, T, H, W, s_n, s_c, s_t,
+      pdl(pack_video_kernel<unsigned char, TO>, grid_for(total), 256, 0, st)((const unsigned char*)src, N, C, T, H, W, s_n, s_c, s_t,
                                                                           s_h, s_w, frame_ptr, sigma, noise, ns_n, ns_c, ns_p,
                                                                           (const StepState*)rng_state, call_id, (TO*)out);
     });
@@ -647,7 +670,7 @@ int mcg_pack_video(const void* src, int src_dtype, int N, int C, int T, int H, i
     dispatch2(src_dtype, out_dtype, [&](auto ti, auto to) {
       using TI = decltype(ti);
       using TO = decltype(to);
-      pack_elem_kernel<TI, TO><<<grid_for(total * C), 256, 0, st>>>((const TI*)src, N, C, T, H, W, s_n, s_c, s_t, s_h, s_w,
+      pdl(pack_elem_kernel<TI, TO>, grid_for(total * C), 256, 0, st)((const TI*)src, N, C, T, H, W, s_n, s_c, s_t, s_h, s_w,
                                                                      (TO*)out);
     });
     MCG_CHECK_LAUNCH("mcg_pack_video(elem)");
@@ -656,7 +679,7 @@ int mcg_pack_video(const void* src, int src_dtype, int N, int C, int T, int H, i
   dispatch2(src_dtype, out_dtype, [&](auto ti, auto to) {
     using TI = decltype(ti);
     using TO = decltype(to);
-    pack_video_kernel<TI, TO><<<grid_for(total), 256, 0, st>>>((const TI*)src, N, C, T, H, W, s_n, s_c, s_t, s_h, s_w,
+    pdl(pack_video_kernel<TI, TO>, grid_for(total), 256, 0, st)((const TI*)src, N, C, T, H, W, s_n, s_c, s_t, s_h, s_w,
                                                                frame_ptr, sigma, noise, ns_n, ns_c, ns_p,
                                                                (const StepState*)rng_state, call_id, (TO*)out);
   });
@@ -678,15 +701,15 @@ int mcg_act_bn_bwd_apply(const void* g, const void* y, long long M, int C, int d
     using TI = decltype(ti);
     using TO = decltype(to);
     if (C % 8 == 0 && 256 % (C / 8) == 0)
-      act_bn_bwd_apply_kernel<TI, TO, 8, true><<<grid_for(M * (C / 8)), 256, 0, st>>>(
+      pdl(act_bn_bwd_apply_kernel<TI, TO, 8, true>, grid_for(M * (C / 8)), 256, 0, st)(
           (const TI*)g, (const TI*)y, M, C, mean, invstd, gamma, scale, shift, act, slope, use_output, dgamma, dbeta,
           inv_m, (TO*)gy);
     else if (C % 8 == 0)
-      act_bn_bwd_apply_kernel<TI, TO, 8, false><<<grid_for(M * (C / 8)), 256, 0, st>>>(
+      pdl(act_bn_bwd_apply_kernel<TI, TO, 8, false>, grid_for(M * (C / 8)), 256, 0, st)(
           (const TI*)g, (const TI*)y, M, C, mean, invstd, gamma, scale, shift, act, slope, use_output, dgamma, dbeta,
           inv_m, (TO*)gy);
     else
-      act_bn_bwd_apply_kernel<TI, TO, 1, false><<<grid_for(M * C), 256, 0, st>>>(
+      pdl(act_bn_bwd_apply_kernel<TI, TO, 1, false>, grid_for(M * C), 256, 0, st)(
           (const TI*)g, (const TI*)y, M, C, mean, invstd, gamma, scale, shift, act, slope, use_output, dgamma, dbeta,
           inv_m, (TO*)gy);
   });
@@ -707,7 +730,7 @@ int mcg_tanh_bwd_video(const void* gv, const void* gi, int g_dtype, const void* 
     using TO = decltype(to);
     dispatch1(gout_dtype, [&](auto td) {
       using TD = decltype(td);
-      tanh_bwd_video_kernel<TG, TO, TD><<<grid_for(total), 256, 0, st>>>((const TG*)gv, (const TG*)gi, (const TO*)out_tn,
+      pdl(tanh_bwd_video_kernel<TG, TO, TD>, grid_for(total), 256, 0, st)((const TG*)gv, (const TG*)gi, (const TO*)out_tn,
                                                                          N, T, HW, C, frame_ptr, (TD*)g_tn);
     });
   });
@@ -729,7 +752,7 @@ int mcg_video_to_uint8(const void* videos, int dtype, int T, int N, int C, int H
   }
   dispatch1(dtype, [&](auto ti) {
     using TI = decltype(ti);
-    video_to_uint8_kernel<TI><<<grid_for(total), 256, 0, st>>>((const TI*)videos, T, N, C, H, W, u8, grid, size);
+    pdl(video_to_uint8_kernel<TI>, grid_for(total), 256, 0, st)((const TI*)videos, T, N, C, H, W, u8, grid, size);
   });
   MCG_CHECK_LAUNCH("mcg_video_to_uint8");
   return 0;
@@ -738,7 +761,7 @@ int mcg_video_to_uint8(const void* videos, int dtype, int T, int N, int C, int H
 int mcg_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float alpha, float beta1,
                   float beta2, float eps, float wd, float grad_scale, const int* t_ptr, void* stream) {
   if (!p || !g || !m || !v || !t_ptr || n <= 0) MCG_FAIL(MCG_ERR_SHAPE, "mcg_adam_step: bad arguments");
-  adam_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, alpha, beta1, beta2,
+  pdl(adam_kernel, grid_for(n), 256, 0, as_stream(stream))(p, g, m, v, (__nv_bfloat16*)p_bf16, n, alpha, beta1, beta2,
                                                           eps, wd, grad_scale, t_ptr);
   MCG_CHECK_LAUNCH("mcg_adam_step");
   return 0;
@@ -746,32 +769,32 @@ int mcg_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, lo
 
 int mcg_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
   if (!src || !dst || n <= 0) MCG_FAIL(MCG_ERR_SHAPE, "mcg_cast_f32_to_bf16: bad arguments");
-  cast_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, n);
+  pdl(cast_kernel, grid_for(n), 256, 0, as_stream(stream))(src, (__nv_bfloat16*)dst, n);
   MCG_CHECK_LAUNCH("mcg_cast_f32_to_bf16");
   return 0;
 }
 
 int mcg_step_state_init(void* state, unsigned long long seed, void* stream) {
   if (!state) MCG_FAIL(MCG_ERR_SHAPE, "mcg_step_state_init: null state");
-  state_init_kernel<<<1, 1, 0, as_stream(stream)>>>((StepState*)state, seed);
+  pdl(state_init_kernel, 1, 1, 0, as_stream(stream))((StepState*)state, seed);
   MCG_CHECK_LAUNCH("mcg_step_state_init");
   return 0;
 }
 int mcg_step_advance(void* state, int T, void* stream) {
   if (!state) MCG_FAIL(MCG_ERR_SHAPE, "mcg_step_advance: null state");
-  state_advance_kernel<<<1, 1, 0, as_stream(stream)>>>((StepState*)state, T);
+  pdl(state_advance_kernel, 1, 1, 0, as_stream(stream))((StepState*)state, T);
   MCG_CHECK_LAUNCH("mcg_step_advance");
   return 0;
 }
 int mcg_randn(float* out, long long n, float sigma, const void* rng_state, int call_id, void* stream) {
   if (!out || !rng_state || n <= 0) MCG_FAIL(MCG_ERR_SHAPE, "mcg_randn: bad arguments");
-  randn_kernel<<<grid_for((n + 3) / 4), 256, 0, as_stream(stream)>>>(out, n, sigma, (const StepState*)rng_state, call_id);
+  pdl(randn_kernel, grid_for((n + 3) / 4), 256, 0, as_stream(stream))(out, n, sigma, (const StepState*)rng_state, call_id);
   MCG_CHECK_LAUNCH("mcg_randn");
   return 0;
 }
 int mcg_randint(int* out, long long n, int high, const void* rng_state, int call_id, void* stream) {
   if (!out || !rng_state || n <= 0 || high <= 0) MCG_FAIL(MCG_ERR_SHAPE, "mcg_randint: bad arguments");
-  randint_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(out, n, high, (const StepState*)rng_state, call_id);
+  pdl(randint_kernel, grid_for(n), 256, 0, as_stream(stream))(out, n, high, (const StepState*)rng_state, call_id);
   MCG_CHECK_LAUNCH("mcg_randint");
   return 0;
 }

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(Geo g, const T* __restri
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         void* __restrict__ out, int out_bf16, int accumulate,
                                                         long long Mrows, int Ncols, long long Kred, long long k_per_split) {
+  pdl_enter();
   __shared__ float As[TK][TM + kPad];
   __shared__ float Bs[TK][TN + kPad];
   const int tid = threadIdx.x;
@@ -153,6 +154,7 @@ template <typename T, int RM, int CPB>
 __global__ void __launch_bounds__(256) fullwin_fprop_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ bias, void* __restrict__ y,
                                                             int out_bf16, int M, int Ncols, int K) {
+  pdl_enter();
   __shared__ float red[8][RM * CPB];
   const int m0 = blockIdx.x * RM, c0 = blockIdx.y * CPB;
   float acc[RM][CPB];
@@ -222,6 +224,7 @@ template <typename T, int RM>
 __global__ void __launch_bounds__(256) fullwin_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w,
                                                             const float* __restrict__ bias, void* __restrict__ dx,
                                                             int out_bf16, int accumulate, int M, int Cout, int K, int Cin) {
+  pdl_enter();
   const int kq = K / 4;
   const long long quads = (long long)((M + RM - 1) / RM) * kq;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
@@ -267,6 +270,7 @@ __global__ void __launch_bounds__(256) fullwin_dgrad_kernel(const T* __restrict_
 template <typename T, int CB>
 __global__ void __launch_bounds__(256) fullwin_wgrad_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                             float* __restrict__ dw, int M, int Cout, int K, int rows_per_split) {
+  pdl_enter();
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= K / 4) return;
   const int k = q * 4, co0 = blockIdx.y * CB;
@@ -330,19 +334,19 @@ int simt_conv(int mode, const mcg_conv_geom* c, const void* a, const void* b_act
     if (mode == kFprop) {
       if (g.Cout >= 16) {   // wide output (G.dc1 backward-data): 8 rows x 4 columns per block
         dim3 grid((unsigned)((g.N + 7) / 8), (unsigned)((g.Cout + 3) / 4));
-        if (dtype == MCG_F32) fullwin_fprop_kernel<float, 8, 4><<<grid, 256, 0, st>>>((const float*)a, w, bias, out, ob, g.N, g.Cout, g.K);
-        else fullwin_fprop_kernel<__nv_bfloat16, 8, 4><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, w, bias, out, ob, g.N, g.Cout, g.K);
+        if (dtype == MCG_F32) pdl(fullwin_fprop_kernel<float, 8, 4>, grid, 256, 0, st)((const float*)a, w, bias, out, ob, g.N, g.Cout, g.K);
+        else pdl(fullwin_fprop_kernel<__nv_bfloat16, 8, 4>, grid, 256, 0, st)((const __nv_bfloat16*)a, w, bias, out, ob, g.N, g.Cout, g.K);
       } else {              // a handful of columns (the discriminators' last layer): one row per block keeps the grid full
         dim3 grid((unsigned)g.N, (unsigned)g.Cout);
-        if (dtype == MCG_F32) fullwin_fprop_kernel<float, 1, 1><<<grid, 256, 0, st>>>((const float*)a, w, bias, out, ob, g.N, g.Cout, g.K);
-        else fullwin_fprop_kernel<__nv_bfloat16, 1, 1><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, w, bias, out, ob, g.N, g.Cout, g.K);
+        if (dtype == MCG_F32) pdl(fullwin_fprop_kernel<float, 1, 1>, grid, 256, 0, st)((const float*)a, w, bias, out, ob, g.N, g.Cout, g.K);
+        else pdl(fullwin_fprop_kernel<__nv_bfloat16, 1, 1>, grid, 256, 0, st)((const __nv_bfloat16*)a, w, bias, out, ob, g.N, g.Cout, g.K);
       }
     } else {
       const int rm = g.N >= 256 ? 8 : 1;   // many rows (G.dc1 forward): share each weight vector between 8 of them
       long long total = (long long)((g.N + rm - 1) / rm) * (g.K / 4);
       long long nb = (total + 255) / 256;
       int blocks = (int)(nb < (long long)num_sms() * 16 ? nb : (long long)num_sms() * 16);
-#define GO_FW(T, RM_) fullwin_dgrad_kernel<T, RM_><<<blocks, 256, 0, st>>>((const T*)a, w, bias, out, ob, accumulate, g.N, g.Cout, g.K, g.Cin)
+#define GO_FW(T, RM_) pdl(fullwin_dgrad_kernel<T, RM_>, blocks, 256, 0, st)((const T*)a, w, bias, out, ob, accumulate, g.N, g.Cout, g.K, g.Cin)
       if (dtype == MCG_F32) { if (rm == 8) GO_FW(float, 8); else GO_FW(float, 1); }
       else { if (rm == 8) GO_FW(__nv_bfloat16, 8); else GO_FW(__nv_bfloat16, 1); }
 #undef GO_FW
@@ -362,7 +366,7 @@ int simt_conv(int mode, const mcg_conv_geom* c, const void* a, const void* b_act
     const int rps = (g.N + splits - 1) / splits;
     splits = (g.N + rps - 1) / rps;
     dim3 grid((unsigned)((quads + 255) / 256), (unsigned)gy, (unsigned)splits);
-#define GO_WG(T, CB_) fullwin_wgrad_kernel<T, CB_><<<grid, 256, 0, st>>>((const T*)a, (const T*)b_act, (float*)out, g.N, g.Cout, g.K, rps)
+#define GO_WG(T, CB_) pdl(fullwin_wgrad_kernel<T, CB_>, grid, 256, 0, st)((const T*)a, (const T*)b_act, (float*)out, g.N, g.Cout, g.K, rps)
     if (dtype == MCG_F32) { if (cb == 8) GO_WG(float, 8); else GO_WG(float, 1); }
     else { if (cb == 8) GO_WG(__nv_bfloat16, 8); else GO_WG(__nv_bfloat16, 1); }
 #undef GO_WG
@@ -392,7 +396,7 @@ int simt_conv(int mode, const mcg_conv_geom* c, const void* a, const void* b_act
   if (gx > 2147483647LL || gy > 65535) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: grid too large", who);
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)splits);
 #define GO(T, MODE)                                                                                             \
-  conv_simt_kernel<T, MODE><<<grid, 256, 0, st>>>(g, (const T*)a, (const T*)b_act, w, bias, out, out_dtype == MCG_BF16, \
+  pdl(conv_simt_kernel<T, MODE>, grid, 256, 0, st)(g, (const T*)a, (const T*)b_act, w, bias, out, out_dtype == MCG_BF16, \
                                                   accumulate, Mrows, Ncols, Kred, kps)
   if (dtype == MCG_F32) {
     if (mode == kFprop) GO(float, kFprop); else if (mode == kDgrad) GO(float, kDgrad); else GO(float, kWgrad);

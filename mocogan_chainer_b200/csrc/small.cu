@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(kGruWarps * 32) gru_forward_kernel(GruPtrs P, 
                                                                      const float* __restrict__ zc, int T, int N, int H,
                                                                      int Zc, float* __restrict__ Z,
                                                                      float* __restrict__ cache) {
+  pdl_enter();
   extern __shared__ float sm[];
   float* W[12];
   const int I = L + H;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(kGruWarps * 32) gru_backward_kernel(GruPtrs P,
                                                                       const float* __restrict__ cache,
                                                                       const float* __restrict__ gz, int T, int N, int H,
                                                                       int Zc) {
+  pdl_enter();
   extern __shared__ float sm[];
   float* W[12];
   const int I = L + H;
@@ -180,6 +182,7 @@ __device__ float ce_row(const float* y, int C, int t, float inv_n, float* g) {
 __global__ void __launch_bounds__(128) loss_dis_kernel(const float* y_real, const float* y_fake, const int* t_real,
                                                        const int* t_fake, int N, int C, int use_ce, float* loss,
                                                        float* gy_real, float* gy_fake) {
+  pdl_enter();
   __shared__ float sh[4];
   const float inv_n = 1.f / (float)N;
   for (int i = threadIdx.x; i < N * C; i += blockDim.x) { gy_real[i] = 0.f; gy_fake[i] = 0.f; }
@@ -203,6 +206,7 @@ __global__ void __launch_bounds__(128) loss_dis_kernel(const float* y_real, cons
 
 __global__ void __launch_bounds__(128) loss_gen_kernel(const float* y_i, const float* y_v, const int* t_fake, int N, int C,
                                                        int use_ce, float* loss, float* gy_i, float* gy_v) {
+  pdl_enter();
   __shared__ float sh[4];
   const float inv_n = 1.f / (float)N;
   for (int i = threadIdx.x; i < N * C; i += blockDim.x) { gy_i[i] = 0.f; gy_v[i] = 0.f; }
@@ -222,7 +226,8 @@ __global__ void __launch_bounds__(128) loss_gen_kernel(const float* y_i, const f
   if (threadIdx.x == 0) *loss = tot;
 }
 
-__global__ void int_add_kernel(int* p, int d) { *p += d; }
+__global__ void int_add_kernel(int* p, int d) {
+  pdl_enter(); *p += d; }
 
 }  // namespace mcg
 
@@ -244,7 +249,7 @@ int mcg_gru_forward(const float* const* params_host, const int* labels, int L, c
   GruPtrs P;
   for (int i = 0; i < 12; ++i) P.p[i] = params_host[i];
   size_t smem = (size_t)(3 * (H * (L + H) + H * H) + 6 * H) * sizeof(float);
-  gru_forward_kernel<<<(N + kGruWarps - 1) / kGruWarps, kGruWarps * 32, smem, as_stream(stream)>>>(
+  pdl(gru_forward_kernel, (N + kGruWarps - 1) / kGruWarps, kGruWarps * 32, smem, as_stream(stream))(
       P, labels, L, h0, eps, zc, T, N, H, Zc, z, cache);
   MCG_CHECK_LAUNCH("mcg_gru_forward");
   return 0;
@@ -260,7 +265,7 @@ int mcg_gru_backward(const float* const* params_host, float* const* grads_host, 
   for (int i = 0; i < 12; ++i) { P.p[i] = params_host[i]; G.p[i] = grads_host[i]; }
   if (H > kGruMaxH) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_gru_backward: H = %d > %d", H, kGruMaxH);
   size_t smem = (size_t)(3 * (H * (L + H) + H * H) + 6 * H) * sizeof(float);
-  gru_backward_kernel<<<(N + kGruWarps - 1) / kGruWarps, kGruWarps * 32, smem, as_stream(stream)>>>(
+  pdl(gru_backward_kernel, (N + kGruWarps - 1) / kGruWarps, kGruWarps * 32, smem, as_stream(stream))(
       P, G, labels, L, eps, cache, gz, T, N, H, Zc);
   MCG_CHECK_LAUNCH("mcg_gru_backward");
   return 0;
@@ -271,7 +276,7 @@ int mcg_loss_dis(const float* y_real, const float* y_fake, const int* t_real, co
   if (!y_real || !y_fake || !loss || !gy_real || !gy_fake || N <= 0 || C <= 0)
     MCG_FAIL(MCG_ERR_SHAPE, "mcg_loss_dis: bad arguments");
   if (use_ce && (!t_real || !t_fake || C < 2)) MCG_FAIL(MCG_ERR_SHAPE, "mcg_loss_dis: CE needs labels and C >= 2");
-  loss_dis_kernel<<<1, 128, 0, as_stream(stream)>>>(y_real, y_fake, t_real, t_fake, N, C, use_ce, loss, gy_real, gy_fake);
+  pdl(loss_dis_kernel, 1, 128, 0, as_stream(stream))(y_real, y_fake, t_real, t_fake, N, C, use_ce, loss, gy_real, gy_fake);
   MCG_CHECK_LAUNCH("mcg_loss_dis");
   return 0;
 }
@@ -280,14 +285,14 @@ int mcg_loss_gen(const float* y_i, const float* y_v, const int* t_fake, int N, i
                  float* gy_i, float* gy_v, void* stream) {
   if (!y_i || !y_v || !loss || !gy_i || !gy_v || N <= 0 || C <= 0) MCG_FAIL(MCG_ERR_SHAPE, "mcg_loss_gen: bad arguments");
   if (use_ce && (!t_fake || C < 2)) MCG_FAIL(MCG_ERR_SHAPE, "mcg_loss_gen: CE needs labels and C >= 2");
-  loss_gen_kernel<<<1, 128, 0, as_stream(stream)>>>(y_i, y_v, t_fake, N, C, use_ce, loss, gy_i, gy_v);
+  pdl(loss_gen_kernel, 1, 128, 0, as_stream(stream))(y_i, y_v, t_fake, N, C, use_ce, loss, gy_i, gy_v);
   MCG_CHECK_LAUNCH("mcg_loss_gen");
   return 0;
 }
 
 int mcg_int_add(int* p, int delta, void* stream) {
   if (!p) MCG_FAIL(MCG_ERR_SHAPE, "mcg_int_add: null pointer");
-  int_add_kernel<<<1, 1, 0, as_stream(stream)>>>(p, delta);
+  pdl(int_add_kernel, 1, 1, 0, as_stream(stream))(p, delta);
   MCG_CHECK_LAUNCH("mcg_int_add");
   return 0;
 }

@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap mapB,
                                                                 const __grid_constant__ TcParams P, void* __restrict__ out,
                                                                 const float* __restrict__ bias) {
+  pdl_launch_dependents();
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
   constexpr int ACC_COLS = MT * BN;                       // fp32 accumulator columns of one tile
@@ -273,6 +274,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  pdl_wait();   // everything above overlapped the predecessor's tail; no global / TMA access before this line
 
   const uint32_t smem_a = smem_u32(smem);
   const uint32_t full_a = smem_u32(&full_bar[0]), empty_a = smem_u32(&empty_bar[0]);
@@ -428,6 +430,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_tr_kernel(const __grid_
                                                                    const __grid_constant__ CUtensorMap mapB,
                                                                    const __grid_constant__ TcParams P, void* __restrict__ out,
                                                                    const float* __restrict__ bias) {
+  pdl_launch_dependents();
   static_assert(MODE == kFprop || MODE == kDgrad, "temporal re-use is for fprop / dgrad");
   constexpr int B_BYTES = BN * 128;
   constexpr int ACC_COLS = MT * BN;
@@ -456,6 +459,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_tr_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  pdl_wait();   // everything above overlapped the predecessor's tail; no global / TMA access before this line
   const uint32_t ringA = smem_u32(smem), ringB = ringA + ASLOTS * aslot_bytes;
   const uint32_t fullA_a = smem_u32(&fullA[0]), emptyA_a = smem_u32(&emptyA[0]);
   const uint32_t fullB_a = smem_u32(&fullB[0]), emptyB_a = smem_u32(&emptyB[0]);
@@ -741,7 +745,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
     if (e != cudaSuccess) MCG_FAIL((int)e, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
     configured = true;
   }
-  tc_conv_kernel<MODE, BN, MT, STAGES><<<grid, kTcThreads, smem, st>>>(ma, mb, P, out, bias);
+  pdl(tc_conv_kernel<MODE, BN, MT, STAGES>, grid, kTcThreads, smem, st)(ma, mb, P, out, bias);
   MCG_CHECK_LAUNCH(who);
   return 0;
 }
@@ -823,7 +827,7 @@ static int launch_tr(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
     if (e != cudaSuccess) MCG_FAIL((int)e, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
     configured = smem;
   }
-  tc_conv_tr_kernel<MODE, BN, MT><<<grid, kTcThreads, smem, st>>>(ma, mb, P, out, bias);
+  pdl(tc_conv_tr_kernel<MODE, BN, MT>, grid, kTcThreads, smem, st)(ma, mb, P, out, bias);
   MCG_CHECK_LAUNCH(who);
   return 0;
 }
@@ -1061,6 +1065,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const __nv_bfloat16* __rest
                                                      long long M, int Kp, int Cin, int Ti, int Hi, int Wi, int To, int Ho,
                                                      int Wo, int kT, int kH, int kW, int sT, int sH, int sW, int pT, int pH,
                                                      int pW) {
+  pdl_enter();
   const int groups = Kp / 8;
   const int K = kT * kH * kW * Cin;
   const long long total = M * groups;
@@ -1094,6 +1099,7 @@ template <int CIN, int KW>
 __global__ void __launch_bounds__(128) im2col_line_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ cols,
                                                           int Kp, int Ti, int Hi, int Wi, int To, int Ho, int Wo, int kT, int kH,
                                                           int sT, int sH, int sW, int pT, int pH, int pW) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned short rows[];  // [kT*kH][L]: 8 zeros | Wi*CIN source values | 8 zeros
   const int runs = kT * kH;
   const int RW = Wi * CIN;                  // launcher guarantees RW % 8 == 0, pW*CIN <= 8, (KW-pW-1)*CIN <= 8
@@ -1147,6 +1153,7 @@ __global__ void __launch_bounds__(128) im2col_line_kernel(const __nv_bfloat16* _
 }
 // wp[co][Kp] = w[co][k] (k < K) else 0
 __global__ void pad_rows_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wp, int rows, int K, int Kp) {
+  pdl_enter();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * Kp; i += gridDim.x * blockDim.x) {
     const int r = i / Kp, k = i % Kp;
     wp[i] = k < K ? w[(long long)r * K + k] : __float2bfloat16_rn(0.f);
@@ -1155,6 +1162,7 @@ __global__ void pad_rows_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat
 // wt[j = (tap, ci), zero-padded to Jp rows][co] = w[co][tap][ci]   (K-major B operand of the dgrad GEMM)
 __global__ void transpose_jk_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wt, int Cout, int J,
                                     int Jp) {
+  pdl_enter();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Jp * Cout; i += gridDim.x * blockDim.x) {
     const int j = i / Cout, co = i % Cout;
     wt[i] = j < J ? w[(long long)co * J + j] : __float2bfloat16_rn(0.f);
@@ -1167,6 +1175,7 @@ __global__ void __launch_bounds__(128) col2im_line_kernel(const __nv_bfloat16* _
                                                           void* __restrict__ dx, int out_f32, long long Mpix, int Cin, int Ti, int Hi,
                                                           int Wi, int To, int Ho, int Wo, int kT, int kH, int kW, int sT, int sH,
                                                           int sW, int pT, int pH, int pW) {
+  pdl_enter();
   // Only the taps whose parity matches this input line can reach it: kt = (ti+pT) % sT + a*sT, kh = (hi+pH) % sH + b*sH.
   // Slot (a, b) of the staging buffer holds that run's Wo*kW*Cin values (zeros when the run falls outside the output);
   // every thread decides that for the vectors it copies, so there is no serial set-up phase.
@@ -1231,6 +1240,7 @@ struct MergedGeom {
 };
 // Wm[row = ((e*sH + a)*sW + b)*Cin + ci (zero rows up to 64)][tap' = (u*nH + v)*nW + q][co]
 __global__ void merged_weights_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wm, MergedGeom G) {
+  pdl_enter();
   const int taps2 = G.nT * G.nH * G.nW;
   const long long total = 64LL * taps2 * G.Cout;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -1259,6 +1269,7 @@ __global__ void merged_weights_kernel(const __nv_bfloat16* __restrict__ w, __nv_
 __global__ void __launch_bounds__(256) depth_to_space_kernel(const __nv_bfloat16* __restrict__ zm, const float* __restrict__ bias,
                                                              void* __restrict__ dx, int out_f32, long long cells, int Cin, int Ti,
                                                              int Hi, int Wi, int L, int I, int J, int sT, int sH, int sW) {
+  pdl_enter();
   const int RUN = sW * Cin, sub = sT * sH;
   const long long total = cells * sub;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -1333,20 +1344,20 @@ int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b
       const long long cells = (long long)g->N * L * I * J;
       __nv_bfloat16* zm = reinterpret_cast<__nv_bfloat16*>(base);
       __nv_bfloat16* wm = reinterpret_cast<__nv_bfloat16*>(base + round_up(cells * 128, 1024));
-      merged_weights_kernel<<<128, 256, 0, st>>>((const __nv_bfloat16*)b, wm, G);
+      pdl(merged_weights_kernel, 128, 256, 0, st)((const __nv_bfloat16*)b, wm, G);
       MCG_CHECK_LAUNCH(who);
       // stride-1 fprop over dy: "input" = dy, window (nT,nH,nW), zero padding -dmin (the far side is TMA out-of-bounds fill)
       mcg_conv_geom g2 = {g->N, g->Cout, 64, g->To, g->Ho, g->Wo, L, I, J, G.nT, G.nH, G.nW, 1, 1, 1, -G.dt_min, -G.dh_min, -G.dw_min};
       if ((rc = tc_conv(kFprop, &g2, a, wm, zm, nullptr, MCG_BF16, st))) return rc;
       long long nb = (cells * g->sT * g->sH + 255) / 256;
       if (nb > (long long)num_sms() * 16) nb = (long long)num_sms() * 16;
-      depth_to_space_kernel<<<(unsigned)nb, 256, 0, st>>>(zm, bias, out, out_dtype == MCG_F32, cells, g->Cin, g->Ti, g->Hi, g->Wi,
+      pdl(depth_to_space_kernel, (unsigned)nb, 256, 0, st)(zm, bias, out, out_dtype == MCG_F32, cells, g->Cin, g->Ti, g->Hi, g->Wi,
                                                          L, I, J, g->sT, g->sH, g->sW);
       MCG_CHECK_LAUNCH(who);
       return 0;
     }
     if (M > 0x7fffffffLL) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: too many pixels", who);
-    transpose_jk_kernel<<<64, 256, 0, st>>>((const __nv_bfloat16*)b, wpad, g->Cout, K, Kp);
+    pdl(transpose_jk_kernel, 64, 256, 0, st)((const __nv_bfloat16*)b, wpad, g->Cout, K, Kp);
     MCG_CHECK_LAUNCH(who);
     mcg_conv_geom g2 = {1, g->Cout, Kp, 1, 1, (int)M, 1, 1, (int)M, 1, 1, 1, 1, 1, 1, 0, 0, 0};
     const int RUN = g->kW * g->Cin;
@@ -1354,7 +1365,7 @@ int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b
     const long long lines = (long long)g->N * g->Ti * g->Hi;
     const size_t smem = (size_t)ceil_div(g->kT, g->sT) * ceil_div(g->kH, g->sH) * g->Wo * g->kW * g->Cin * 2;
     if (lines > 0x7fffffffLL || smem > 48 * 1024 || (g->Wo * g->kW * g->Cin) % 8) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: line too large", who);
-    col2im_line_kernel<<<(unsigned)lines, 128, smem, st>>>(cols, bias, out, out_dtype == MCG_F32, M, g->Cin, g->Ti, g->Hi, g->Wi,
+    pdl(col2im_line_kernel, (unsigned)lines, 128, smem, st)(cols, bias, out, out_dtype == MCG_F32, M, g->Cin, g->Ti, g->Hi, g->Wi,
                                                            g->To, g->Ho, g->Wo, g->kT, g->kH, g->kW, g->sT, g->sH, g->sW, g->pT,
                                                            g->pH, g->pW);
     MCG_CHECK_LAUNCH(who);
@@ -1368,13 +1379,13 @@ int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b
     const bool line_ok = lines < 0x7fffffffLL && smem <= 48 * 1024 && (g->Wi * g->Cin) % 8 == 0 && g->pW * g->Cin <= 8 &&
                          (g->kW - g->pW - 1) * g->Cin <= 8 && (g->Wo - 1) * g->sW - g->pW + g->kW - 1 <= g->Wi + (8 / g->Cin) - 1;
     if (g->kW == 4 && g->Cin == 3 && line_ok)
-      im2col_line_kernel<3, 4><<<(unsigned)lines, 128, smem, st>>>((const __nv_bfloat16*)x, cols, Kp, g->Ti, g->Hi, g->Wi, g->To, g->Ho,
+      pdl(im2col_line_kernel<3, 4>, (unsigned)lines, 128, smem, st)((const __nv_bfloat16*)x, cols, Kp, g->Ti, g->Hi, g->Wi, g->To, g->Ho,
                                                                    g->Wo, g->kT, g->kH, g->sT, g->sH, g->sW, g->pT, g->pH, g->pW);
     else if (g->kW == 4 && g->Cin == 1 && line_ok)
-      im2col_line_kernel<1, 4><<<(unsigned)lines, 128, smem, st>>>((const __nv_bfloat16*)x, cols, Kp, g->Ti, g->Hi, g->Wi, g->To, g->Ho,
+      pdl(im2col_line_kernel<1, 4>, (unsigned)lines, 128, smem, st)((const __nv_bfloat16*)x, cols, Kp, g->Ti, g->Hi, g->Wi, g->To, g->Ho,
                                                                    g->Wo, g->kT, g->kH, g->sT, g->sH, g->sW, g->pT, g->pH, g->pW);
     else
-      im2col_kernel<<<num_sms() * 16, 256, 0, st>>>((const __nv_bfloat16*)x, cols, M, Kp, g->Cin, g->Ti, g->Hi, g->Wi, g->To, g->Ho,
+      pdl(im2col_kernel, num_sms() * 16, 256, 0, st)((const __nv_bfloat16*)x, cols, M, Kp, g->Cin, g->Ti, g->Hi, g->Wi, g->To, g->Ho,
                                                      g->Wo, g->kT, g->kH, g->kW, g->sT, g->sH, g->sW, g->pT, g->pH, g->pW);
   }
   MCG_CHECK_LAUNCH(who);
@@ -1383,7 +1394,7 @@ int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b
   if (mode == kFprop) {
     const void* wk = b;
     if (Kp != K) {
-      pad_rows_kernel<<<32, 256, 0, st>>>((const __nv_bfloat16*)b, wpad, g->Cout, K, Kp);
+      pdl(pad_rows_kernel, 32, 256, 0, st)((const __nv_bfloat16*)b, wpad, g->Cout, K, Kp);
       MCG_CHECK_LAUNCH(who);
       wk = wpad;
     }

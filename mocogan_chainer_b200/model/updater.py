@@ -64,13 +64,9 @@ class Updater(chainer.training.StandardUpdater):
                 self.tf_writer.add_scalar('loss:{}'.format(link.name), float(loss.data), self.epoch)
 
     def concat_label_video(self, video, label, xp=None):
-        """updater.py:65-76 (cgan): append dim_zl planes of -1 with +1 at the label plane."""
-        v = video.data if isinstance(video, Variable) else video
-        lab = label.data if isinstance(label, Variable) else label
-        N, C, T, H, W = v.shape
-        planes = -torch.ones((N, self.dim_zl, T, H, W), dtype=v.dtype, device=v.device)
-        planes[torch.arange(N, device=v.device), lab.long()] = 1.
-        return Variable(torch.cat((v, planes), dim=1), requires_grad=False)
+        """updater.py:65-76 (cgan): append dim_zl planes of -1 with +1 at the label plane.  A FunctionNode, so the fake
+        clip stays attached to the generator (F.concat in the reference)."""
+        return F.concat_label_video(video, label, self.dim_zl)
 
     # ------------------------------------------------------------------ one step on device-resident inputs
     def step_on_device(self, x_real, t_real):
@@ -117,8 +113,11 @@ class Updater(chainer.training.StandardUpdater):
                 x_fake, t_fake = image_gen(batchsize)         # updater.py:101  (T,N,C,H,W)
                 x_fake = x_fake.transpose(1, 2, 0, 3, 4)      # updater.py:102  (N,C,T,H,W), still attached to G
             t_fake = None if t_fake is None else Variable(t_fake, requires_grad=False)
+            x_gen = x_fake                                # what passes A/B must not back-propagate past
             if self.model == 'cgan':
-                raise NotImplementedError("cgan needs the label planes on the attached fake clip (SURVEY.md §8f rank 4)")
+                with torch.cuda.stream(st_g):
+                    x_fake = self.concat_label_video(x_fake, t_fake)   # updater.py:104-106
+                x_gen = x_fake
             st_di.wait_stream(st_g)
             with torch.cuda.stream(st_di):
                 y_fake_i = image_dis(x_fake, frame=t)     # updater.py:107
@@ -132,7 +131,7 @@ class Updater(chainer.training.StandardUpdater):
             # reference (image_gen.cleargrads() in pass C) -> not computed.  pass C: discriminator wgrads are discarded.
             # Passes A and B touch disjoint parameters and activations, so A runs on `di` while B runs on the caller's
             # stream (+ `dvf`); both are complete before pass C reads the updated discriminator weights.
-            image_dis_optimizer.stop_variables = video_dis_optimizer.stop_variables = (x_fake,)
+            image_dis_optimizer.stop_variables = video_dis_optimizer.stop_variables = (x_gen,)
             image_gen_optimizer.frozen_links = (image_dis, video_dis)
             with torch.cuda.stream(st_di):
                 image_dis_optimizer.update(self.loss_dis, image_dis, y_real_i, y_fake_i, t_real, t_fake)

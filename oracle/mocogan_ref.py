@@ -263,9 +263,22 @@ def loss_gen(model, y_fake_i, y_fake_v, t_fake):
 # ================================================================================================
 # Updater.update_core  (updater.py:78-113)
 # ================================================================================================
+def concat_label_video(video, label, dim_zl):
+    """updater.py:65-76 (cgan): dim_zl planes of -1 with +1 at each clip's label plane, appended on the channel axis.
+    (N,C,T,H,W) -> (N,C+dim_zl,T,H,W).  The reference indexes with a Variable (`label_video[np.arange(N), label]`),
+    which Chainer v3 rejects (SURVEY.md App. B#9); this is what the line means with `label` as an integer array."""
+    N, C, T, H, W = video.shape
+    label_video = -1.0 * np.ones((N, dim_zl, T, H, W), dtype=video.dtype)
+    label_video[np.arange(N), np.asarray(label).astype(np.int64)] = 1.
+    return np.concatenate((video, label_video), axis=1)
+
+
 def draw_step_randoms(rng_lat, rng_noise, gen, image_dis, video_dis, batchsize, x_shape, t=None, dtype=np.float32):
-    """All random tensors one step consumes, in the reference's draw order (SURVEY.md §3.2 pt 5)."""
+    """All random tensors one step consumes, in the reference's draw order (SURVEY.md §3.2 pt 5).  `x_shape` is the
+    clip's; the discriminators' input noise takes THEIR channel count (cgan: clip + label planes, updater.py:93-95)."""
     N, C, T, H, W = x_shape
+    C = image_dis.in_channels
+    x_shape = (N, C, T, H, W)
     r = {}
     r["t"] = int(rng_noise.integers(0, T)) if t is None else int(t)
     r["noise_i_real"] = [rng_noise.standard_normal(s).astype(dtype) for s in image_dis.noise_shapes((N, C, H, W))]
@@ -298,12 +311,18 @@ class Updater:
         N = x_real.shape[0]
         t = r["t"]
         t_real = None if t_real is None else np.asarray(t_real).astype(np.int64)
+        cgan = self.model == "cgan"
+        Cx = x_real.shape[1]
+        if cgan:   # updater.py:93-95
+            x_real = concat_label_video(x_real, t_real, G.dim_zl)
         # forward — updater.py:97-108
         y_real_i, c_ri = Di.forward(x_real[:, :, t], r["noise_i_real"])
         y_real_v, c_rv = Dv.forward(x_real, r["noise_v_real"])
         x_fake_tn, c_g = G.forward(N, r["latents"])
         t_fake = r["latents"]["labels"]
         x_fake = x_fake_tn.transpose(1, 2, 0, 3, 4)  # (N,C,T,H,W), not detached
+        if cgan:   # updater.py:104-106: F.concat -> its backward hands the clip channels' slice to the generator
+            x_fake = concat_label_video(x_fake, t_fake, G.dim_zl)
         y_fake_i, c_fi = Di.forward(x_fake[:, :, t], r["noise_i_fake"])
         y_fake_v, c_fv = Dv.forward(x_fake, r["noise_v_fake"])
         if trace is not None:
@@ -312,7 +331,7 @@ class Updater:
                          cache_fv=c_fv)
 
         def dead_generator_backward(gx_fake_nct):
-            G.backward(c_g, gx_fake_nct.transpose(2, 0, 1, 3, 4))
+            G.backward(c_g, gx_fake_nct[:, :Cx].transpose(2, 0, 1, 3, 4))
 
         # PASS A — updater.py:111
         loss_di, gr, gf = loss_dis(self.model, Di.name, y_real_i, y_fake_i, t_real, t_fake)
@@ -342,6 +361,7 @@ class Updater:
         _, gx_v = Dv.backward(c_fv, gv, need_gx=True, need_gw=as_executed)
         gx_fake = gx_v.copy()
         gx_fake[:, :, t] += gx_i
+        gx_fake = gx_fake[:, :Cx]   # cgan: the label planes are constants
         grads_g = G.backward(c_g, gx_fake.transpose(2, 0, 1, 3, 4))
         self.opt["image_gen"].update(G.params, grads_g)
         if trace is not None:
@@ -350,7 +370,7 @@ class Updater:
 
 
 def build_models(config, dtype=np.float32, seed=0, n_filters=64):
-    """config: 'mnist_normal' (BASELINE config 1), 'mug_normal' (2/3), 'mug_infogan' (4)."""
+    """config: 'mnist_normal' (BASELINE config 1), 'mug_normal' (2/3), 'mug_infogan' (4), 'mug_cgan' (train.py:74-79)."""
     rng = np.random.default_rng(seed)
     if config == "mnist_normal":
         C, zl, out, model = 1, 0, 1, "normal"
@@ -358,11 +378,14 @@ def build_models(config, dtype=np.float32, seed=0, n_filters=64):
         C, zl, out, model = 3, 6, 1, "normal"
     elif config == "mug_infogan":
         C, zl, out, model = 3, 6, 7, "infogan"
+    elif config == "mug_cgan":
+        C, zl, out, model = 3, 6, 1, "cgan"
     else:
         raise ValueError(config)
+    Cd = C + zl if model == "cgan" else C
     G = ImageGenerator(50, 10, zl, C, n_filters, 16, rng=rng, dtype=dtype)
-    Di = ImageDiscriminator(C, out, n_filters, True, 0.2, rng=rng, dtype=dtype)
-    Dv = VideoDiscriminator(C, out, n_filters, True, 0.2, rng=rng, dtype=dtype)
+    Di = ImageDiscriminator(Cd, out, n_filters, True, 0.2, rng=rng, dtype=dtype)
+    Dv = VideoDiscriminator(Cd, out, n_filters, True, 0.2, rng=rng, dtype=dtype)
     return model, G, Di, Dv
 
 

@@ -195,3 +195,32 @@ def test_uint8_clip_cache_follows_datasets_py():
     # linspace branch really subsamples: frames two apart
     idx = ref.subsequence_indices(40, 16, 2, lambda gap: 3)
     assert idx[0] == 3 and idx[-1] == 33 and np.all(np.diff(idx) == 2)
+
+
+def test_concat_label_video_node_matches_oracle_and_slices_the_video_gradient():
+    """updater.py:65-76 / :104-106 (cgan): the node's clip + label planes equal the oracle's, on a generator-style
+    transposed view; backward keeps only the clip channels of both halves of the lazy video gradient."""
+    from mocogan_chainer_b200.chainer import VideoGrad
+    from mocogan_chainer_b200.chainer import functions as F
+    from oracle import mocogan_ref as ref
+    rng = np.random.default_rng(0)
+    T, N, C, H, W, L = 4, 3, 3, 2, 2, 6
+    x_tn = torch.from_numpy(rng.standard_normal((T, N, C, H, W)).astype(np.float32))
+    lab = torch.tensor([5, 0, 2], dtype=torch.int32)
+    x = Variable(x_tn.permute(1, 2, 0, 3, 4))                    # updater.py:102, a strided view
+    y = F.concat_label_video(x, Variable(lab, requires_grad=False), L)
+    want = ref.concat_label_video(x.data.numpy(), lab.numpy(), L)
+    assert tuple(y.shape) == (N, C + L, T, H, W) and y.requires_grad
+    assert np.array_equal(y.data.numpy(), want)
+    assert F.physical_view(y.data).is_contiguous()               # channels-last storage for the input pass
+    gv = torch.from_numpy(rng.standard_normal((N, T, H, W, C + L)).astype(np.float32))
+    gi = torch.from_numpy(rng.standard_normal((N, 1, H, W, C + L)).astype(np.float32))
+    fp = torch.tensor([1], dtype=torch.int32)
+    out, = y.creator_node.backward((0,), (VideoGrad(gv=gv, gi=gi, frame_ptr=fp),))
+    assert out.frame_ptr is fp and out.gv.is_contiguous() and out.gi.is_contiguous()
+    assert torch.equal(out.gv, gv[..., :C]) and torch.equal(out.gi, gi[..., :C])
+    # a real (uint8, unattached) clip is normalised as datasets.py:91 does and needs no gradient
+    u8 = torch.from_numpy(rng.integers(0, 256, size=(N, C, T, H, W), dtype=np.uint8))
+    yr = F.concat_label_video(Variable(u8, requires_grad=False), lab, L)
+    assert not yr.requires_grad
+    assert np.array_equal(yr.data.numpy(), ref.concat_label_video((u8.numpy().astype(np.float32) - 128.) / 128., lab.numpy(), L))

@@ -14,7 +14,7 @@ def _relerr(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
 
 
-@pytest.mark.parametrize("config", ["mnist_normal", "mug_normal", "mug_infogan"])
+@pytest.mark.parametrize("config", ["mnist_normal", "mug_normal", "mug_infogan", "mug_cgan"])
 def test_step_matches_torch_autograd(config):
     nf, N = 4, 3
     model, G, Di, Dv = ref.build_models(config, dtype=np.float64, seed=3, n_filters=nf)

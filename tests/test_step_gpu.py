@@ -37,8 +37,8 @@ def build_pair(config, n_filters, dtype_mode, seed=3):
                 v += 0.1 * prng.standard_normal(v.shape)
     C = oG.out_channels
     G = ImageGenerator(50, 10, oG.dim_zl, C, n_filters, 16)
-    Di = ImageDiscriminator(C, oI.out_channels, n_filters, True, 0.2)
-    Dv = VideoDiscriminator(C, oV.out_channels, n_filters, True, 0.2)
+    Di = ImageDiscriminator(oI.in_channels, oI.out_channels, n_filters, True, 0.2)   # cgan: clip + label planes
+    Dv = VideoDiscriminator(oV.in_channels, oV.out_channels, n_filters, True, 0.2)
     for mine, theirs in ((G, oG), (Di, oI), (Dv, oV)):
         mine.arena()
         for path, p in mine.namedparams():
@@ -173,6 +173,16 @@ def test_step_fp32_strict_mnist_shape():
 
 def test_step_fp32_strict_infogan():
     run_step_case("mug_infogan", 8, 2, "fp32", 1e-5, 1e-4)
+
+
+def test_step_fp32_strict_cgan():
+    """--model cgan (train.py:74-79, updater.py:65-76,93-95,104-106): label planes on the real AND the attached fake
+    clip, 9-channel discriminators, the generator receives the clip channels' slice of the video gradient."""
+    run_step_case("mug_cgan", 8, 2, "fp32", 1e-5, 1e-4)
+
+
+def test_step_bf16_tcgen05_cgan():
+    run_step_case("mug_cgan", 64, 2, "bf16", 2e-2, 0.75)
 
 
 def test_step_bf16_tcgen05_mug_normal():

@@ -95,14 +95,24 @@ def torch_step(model, G, Di, Dv, x_real, t_real, r):
     fl = lambda lst: [f(a) for a in lst]
     x_real = f(x_real)
     N, t = x_real.shape[0], r["t"]
+    t_fake = None if r["latents"]["labels"] is None else torch.from_numpy(r["latents"]["labels"])
+    t_real_t = None if t_real is None else torch.from_numpy(np.asarray(t_real).astype(np.int64))
+
+    def with_labels(video, label):   # updater.py:65-76 written independently: one-hot planes mapped {0,1} -> {-1,+1}
+        onehot = F.one_hot(label.long(), G.dim_zl).to(video.dtype) * 2.0 - 1.0
+        planes = onehot[:, :, None, None, None].expand(-1, -1, *video.shape[2:])
+        return torch.cat((video, planes), dim=1)
+
+    if model == "cgan":
+        x_real = with_labels(x_real, t_real_t)
     y_real_i = dis_forward(PI, x_real[:, :, t], fl(r["noise_i_real"]), Di.noise_sigma, 2, Di.strides, Di.pads)
     y_real_v = dis_forward(PV, x_real, fl(r["noise_v_real"]), Dv.noise_sigma, 3, Dv.strides, Dv.pads)
     x_fake_tn = gen_forward(PG, G, N, r["latents"])
     x_fake = x_fake_tn.permute(1, 2, 0, 3, 4)
+    if model == "cgan":
+        x_fake = with_labels(x_fake, t_fake)
     y_fake_i = dis_forward(PI, x_fake[:, :, t], fl(r["noise_i_fake"]), Di.noise_sigma, 2, Di.strides, Di.pads)
     y_fake_v = dis_forward(PV, x_fake, fl(r["noise_v_fake"]), Dv.noise_sigma, 3, Dv.strides, Dv.pads)
-    t_fake = None if r["latents"]["labels"] is None else torch.from_numpy(r["latents"]["labels"])
-    t_real_t = None if t_real is None else torch.from_numpy(np.asarray(t_real).astype(np.int64))
 
     def loss_dis(name, y_real, y_fake):
         loss = F.softplus(-y_real[:1]).sum() / N + F.softplus(y_fake)[:1].sum() / N
