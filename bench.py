@@ -216,6 +216,68 @@ def time_conv_layers(K, torch, peaks):
     return rows
 
 
+def time_stream_kernels(K, torch, peaks):
+    """HBM-bound passes of the step ("which roofline": K5/K8/K10/K11), each timed ALONE with CUDA events on
+    tensors larger than L2 (the generator's widest BatchNorm layer, G.bn4: 35*16 frames x 32x32 pixels x 64 channels =
+    73 MB in bf16; Adam on the video discriminator's 11.06 M parameters).  achieved = ALGORITHMIC bytes (every operand
+    read or written once) / time, against the measured copy bandwidth."""
+    M, C = 35 * 16 * 32 * 32, 64
+    dev = "cuda"
+    y = torch.randn((M, C), device=dev).bfloat16()
+    g = torch.randn((M, C), device=dev).bfloat16()
+    out = torch.empty_like(y)
+    vec = lambda v: torch.full((C,), v, device=dev)
+    mean, invstd, scale, shift, gamma = vec(0.1), vec(0.9), vec(0.9), vec(-0.09), vec(1.0)
+    dgam, dbet = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    am, av = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    n_adam = 11_060_000 // 8 * 8
+    p32, g32 = torch.randn(n_adam, device=dev), torch.randn(n_adam, device=dev) * 1e-3
+    m32, v32 = torch.zeros(n_adam, device=dev), torch.zeros(n_adam, device=dev)
+    pb16 = torch.empty(n_adam, device=dev, dtype=torch.bfloat16)
+    t_dev = torch.ones(1, dtype=torch.int32, device=dev)
+    eb = y.element_size()
+    cases = [
+        ("bn_stats (colreduce + finalize)", "G.bn4 fwd", M * C * eb,
+         lambda: K.bn_stats(y, M, C, gamma, shift, 2e-5, 0.9, mean, invstd, scale, shift, am, av)),
+        ("affine_act_noise (BN apply + ReLU)", "G.bn4 fwd", 2 * M * C * eb,
+         lambda: K.affine_act_noise(y, M, C, 32 * 32, scale, shift, K.ACT_RELU, 0.2, 0.0, None, None, None, 0, out)),
+        ("act_bn_bwd_reduce (colreduce + finalize)", "G.bn4 bwd", 2 * M * C * eb,
+         lambda: K.act_bn_bwd_reduce(g, y, M, C, mean, invstd, scale, shift, K.ACT_RELU, 0.2, dgam, dbet, None, None)),
+        ("act_bn_bwd_apply", "G.bn4 bwd", 3 * M * C * eb,
+         lambda: K.act_bn_bwd_apply(g, y, M, C, mean, invstd, gamma, scale, shift, K.ACT_RELU, 0.2, 0, dgam, dbet, out)),
+        ("adam_kernel (Adam + WeightDecay + bf16 copy)", "video_dis", 30 * n_adam,
+         lambda: K.adam_step(p32, g32, m32, v32, pb16, 2e-4, 5e-5, 0.999, 1e-8, 1e-5, 1.0, t_dev)),
+    ]
+    rows = []
+    for name, layer, nbytes, fn in cases:
+        # 20 back-to-back launches replayed from a CUDA graph: these kernels run 25-70 us, less than the host needs to issue
+        # one through ctypes, so an eager loop would time the host
+        reps = 20
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(reps):
+                fn()
+        graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = nbytes / ms / 1e6
+        rows.append({"kernel": name, "layer": layer, "ms": ms, "algorithmic_mb": nbytes / 1e6, "gb_per_s": gbs,
+                     "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]})
+    return rows
+
+
 def gen_frames_per_s(torch, peaks, batch=256, video_len=32, iters=8):
     """BASELINE config 5 (generate_samples inference): generator only, batch 256 clips of 32 frames, BatchNorm in
     batch-statistics mode as generate_samples.py runs it, plus the uint8 / grid post-processing.  64x64 frames: the
@@ -317,9 +379,10 @@ def run_ours(args):
     assert K.tc_error_flag() == 0, "a tcgen05 kernel reported an mbarrier timeout"
     assert np.isfinite(loss_sink), "non-finite loss"
 
-    layer_rows, dominant, cpu, gen = None, None, None, None
+    layer_rows, stream_rows, dominant, cpu, gen = None, None, None, None, None
     if rank == 0:
         layer_rows = time_conv_layers(K, torch, peaks)
+        stream_rows = time_stream_kernels(K, torch, peaks)
         tot = {}
         for r in layer_rows:
             tot[(r["kernel"], r["layer"])] = r["ms"] * r["calls_per_step"]
@@ -361,7 +424,9 @@ def run_ours(args):
                               "peak_sustained": peaks["bf16_sustained"],
                               "frac": USEFUL_GF_PER_STEP * steps_per_s / world / 1e3 / peaks["bf16_sustained"],
                               "tc_conv_ms_per_step_isolated": conv_ms},
-                     "layers": layer_rows},
+                     "layers": layer_rows,
+                     "hbm_kernels": {"peak_gb_per_s": peaks["hbm_gbs"], "peak_source": peaks["src"] + " (copy bandwidth)",
+                                     "kernels": stream_rows}},
         "cpu_baseline": cpu,
         "gen": gen,
     }

@@ -122,6 +122,57 @@ template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat
     v[2 * i + 1] = f.y;
   }
 }
+// The same 8 elements held as loaded (4 registers for bf16, 8 for fp32): a streaming kernel issues the loads of several
+// rows back to back and converts afterwards, so every thread keeps 64-128 B in flight instead of 16-32 B.  With 2-4
+// resident blocks per SM that is the ~64 KB per SM HBM3e needs; one row per iteration left these kernels at 40-60 % of
+// the measured copy bandwidth.
+template <typename T> struct Raw8;
+template <> struct Raw8<float> { float4 a, b; };
+template <> struct Raw8<__nv_bfloat16> { uint4 u; };
+template <typename T> __device__ __forceinline__ Raw8<T> ldraw8(const T* p);
+template <> __device__ __forceinline__ Raw8<float> ldraw8<float>(const float* p) {
+  Raw8<float> r;
+  r.a = *reinterpret_cast<const float4*>(p);
+  r.b = *reinterpret_cast<const float4*>(p + 4);
+  return r;
+}
+template <> __device__ __forceinline__ Raw8<__nv_bfloat16> ldraw8<__nv_bfloat16>(const __nv_bfloat16* p) {
+  Raw8<__nv_bfloat16> r;
+  r.u = *reinterpret_cast<const uint4*>(p);
+  return r;
+}
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+__device__ __forceinline__ void unpack8(const Raw8<__nv_bfloat16>& r, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+// Rows in flight per thread / minimum resident blocks per SM (= register cap) of the three hot streaming kernels; the
+// defaults are the best whole-step combination of profiles/r01_stream_kernels_ab.txt.  A kernel that is fastest ALONE
+// (many rows in flight, 128 registers) is not the fastest inside the 4-stream step: its blocks must fit beside a
+// persistent convolution CTA (38 K of the SM's 64 K registers), so the register cap matters more than the unroll.
+#ifndef MCG_RED_U
+#define MCG_RED_U 4
+#endif
+#ifndef MCG_AFF_U
+#define MCG_AFF_U 1
+#endif
+#ifndef MCG_AFF_MB
+#define MCG_AFF_MB 3
+#endif
+#ifndef MCG_APP_U
+#define MCG_APP_U 1
+#endif
+#ifndef MCG_APP_MB
+#define MCG_APP_MB 3
+#endif
+
 template <typename T> __device__ __forceinline__ void st8(T* p, const float (&v)[8]);
 template <> __device__ __forceinline__ void st8<float>(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);

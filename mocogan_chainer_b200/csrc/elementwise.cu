@@ -40,12 +40,10 @@ static int pow2_ge(int x) {
 struct StatsF {  // sum y, sum y^2
   template <int VEC> struct Regs {};
   template <int VEC> __device__ __forceinline__ void prep(int, Regs<VEC>&) const {}
-  template <typename T, int VEC>
-  __device__ __forceinline__ void operator()(const T* y, const T*, long long off, const Regs<VEC>&, float (&a)[VEC],
-                                             float (&b)[VEC]) const {
-    float v[VEC];
-    if (VEC == 8) ld8<T>(y + off, reinterpret_cast<float(&)[8]>(v));
-    else v[0] = ld<T>(y, off);
+  static constexpr bool kTwo = false;
+  template <int VEC>
+  __device__ __forceinline__ void acc(const float (&v)[VEC], const float (&)[VEC], const Regs<VEC>&, float (&a)[VEC],
+                                      float (&b)[VEC]) const {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) { a[i] += v[i]; b[i] += v[i] * v[i]; }
   }
@@ -53,16 +51,17 @@ struct StatsF {  // sum y, sum y^2
 struct SumF {  // sum g
   template <int VEC> struct Regs {};
   template <int VEC> __device__ __forceinline__ void prep(int, Regs<VEC>&) const {}
-  template <typename T, int VEC>
-  __device__ __forceinline__ void operator()(const T* g, const T*, long long off, const Regs<VEC>&, float (&a)[VEC],
-                                             float (&b)[VEC]) const {
-    float v[VEC];
-    if (VEC == 8) ld8<T>(g + off, reinterpret_cast<float(&)[8]>(v));
-    else v[0] = ld<T>(g, off);
+  static constexpr bool kTwo = false;
+  template <int VEC>
+  __device__ __forceinline__ void acc(const float (&v)[VEC], const float (&)[VEC], const Regs<VEC>&, float (&a)[VEC],
+                                      float (&)[VEC]) const {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) a[i] += v[i];
   }
 };
+// ACT >= 0 fixes the activation at compile time (the hot layers: the runtime switch per element made these passes
+// instruction-issue-bound, ~40 instructions per element); ACT = -1 keeps the runtime code.
+template <int ACT>
 struct BnBwdF {  // sum g', sum g'*xhat with g' = g * act'(scale*y+shift)
   const float *mean, *invstd, *scale, *shift;
   int act;
@@ -74,21 +73,14 @@ struct BnBwdF {  // sum g', sum g'*xhat with g' = g * act'(scale*y+shift)
       r.mean[i] = mean[c0 + i]; r.invstd[i] = invstd[c0 + i]; r.scale[i] = scale[c0 + i]; r.shift[i] = shift[c0 + i];
     }
   }
-  template <typename T, int VEC>
-  __device__ __forceinline__ void operator()(const T* g, const T* y, long long off, const Regs<VEC>& r, float (&a)[VEC],
-                                             float (&b)[VEC]) const {
-    float gv[VEC], yv[VEC];
-    if (VEC == 8) {
-      ld8<T>(g + off, reinterpret_cast<float(&)[8]>(gv));
-      ld8<T>(y + off, reinterpret_cast<float(&)[8]>(yv));
-    } else {
-      gv[0] = ld<T>(g, off);
-      yv[0] = ld<T>(y, off);
-    }
+  static constexpr bool kTwo = true;
+  template <int VEC>
+  __device__ __forceinline__ void acc(const float (&gv)[VEC], const float (&yv)[VEC], const Regs<VEC>& r, float (&a)[VEC],
+                                      float (&b)[VEC]) const {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       float pre = r.scale[i] * yv[i] + r.shift[i];
-      float gp = gv[i] * act_grad(act, slope, pre, 0);
+      float gp = gv[i] * act_grad(ACT >= 0 ? ACT : act, slope, pre, 0);
       a[i] += gp;
       b[i] += gp * (yv[i] - r.mean[i]) * r.invstd[i];
     }
@@ -111,16 +103,37 @@ __global__ void __launch_bounds__(kRedThreads) colreduce_kernel(F f, const T* p0
     f.template prep<VEC>(tx * VEC, regs);
     const long long step = (long long)gridDim.x * rpb;
     long long m = (long long)blockIdx.x * rpb + ty;
-    float a2[VEC], b2[VEC];
+    const long long col = (long long)tx * VEC;
+    if constexpr (VEC == 8) {
+      // MCG_RED_U rows per iteration: all loads first (raw, 16-32 B each), arithmetic afterwards
+      constexpr int U = MCG_RED_U;
+      for (; m + (U - 1) * step < M; m += U * step) {
+        Raw8<T> r0[U], r1[U];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) a2[i] = b2[i] = 0.f;
-    for (; m + step < M; m += 2 * step) {   // two independent rows in flight per thread
-      f.template operator()<T, VEC>(p0, p1, m * C + (long long)tx * VEC, regs, a, b);
-      f.template operator()<T, VEC>(p0, p1, (m + step) * C + (long long)tx * VEC, regs, a2, b2);
+        for (int u = 0; u < U; ++u) {
+          r0[u] = ldraw8<T>(p0 + (m + u * step) * C + col);
+          if (F::kTwo) r1[u] = ldraw8<T>(p1 + (m + u * step) * C + col);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float v0[8], v1[8];
+          unpack8(r0[u], v0);
+          if (F::kTwo) unpack8(r1[u], v1);
+          f.template acc<VEC>(reinterpret_cast<const float(&)[VEC]>(v0), reinterpret_cast<const float(&)[VEC]>(v1), regs, a, b);
+        }
+      }
     }
-    if (m < M) f.template operator()<T, VEC>(p0, p1, m * C + (long long)tx * VEC, regs, a, b);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { a[i] += a2[i]; b[i] += b2[i]; }
+    for (; m < M; m += step) {
+      float v0[VEC], v1[VEC];
+      if (VEC == 8) {
+        ld8<T>(p0 + m * C + col, reinterpret_cast<float(&)[8]>(v0));
+        if (F::kTwo) ld8<T>(p1 + m * C + col, reinterpret_cast<float(&)[8]>(v1));
+      } else {
+        v0[0] = ld<T>(p0, m * C + col);
+        if (F::kTwo) v1[0] = ld<T>(p1, m * C + col);
+      }
+      f.template acc<VEC>(v0, v1, regs, a, b);
+    }
   }
   float* mine = red + ((size_t)ty * tpr + tx) * 2 * VEC;
 #pragma unroll
@@ -148,11 +161,23 @@ static int launch_colreduce(F f, const void* p0, const void* p1, long long M, in
   const int tpr = pow2_ge(CG);
   const int rpb = kRedThreads / tpr;
   long long want = (M + (long long)rpb * 8 - 1) / ((long long)rpb * 8);  // >= 8 rows per thread: few partials to finalize
-  int nblk = (int)(want < kRedMaxBlocks ? want : kRedMaxBlocks);
+  size_t smem = (size_t)kRedThreads * 2 * VEC * sizeof(float);
+  // one wave: as many blocks as are resident at once for THIS instantiation (3 per SM for the BatchNorm-backward sums at
+  // 85 registers, 4 for the statistics) — 592 blocks of a 3-per-SM kernel ran as a full wave plus a third of one
+  int cap = kRedMaxBlocks;
+  {
+    int per_sm = 0;
+    cudaError_t e = cudaSuccess;
+    if (dtype == MCG_F32) e = VEC == 8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<float, 8, F>, kRedThreads, smem)
+                                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<float, 1, F>, kRedThreads, smem);
+    else e = VEC == 8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<__nv_bfloat16, 8, F>, kRedThreads, smem)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<__nv_bfloat16, 1, F>, kRedThreads, smem);
+    if (e == cudaSuccess && per_sm > 0 && per_sm * num_sms() < cap) cap = per_sm * num_sms();
+  }
+  int nblk = (int)(want < cap ? want : cap);
   if (nblk < 1) nblk = 1;
   if (ws_bytes < (size_t)nblk * 2 * C * sizeof(float) || !ws)
     MCG_FAIL(MCG_ERR_WORKSPACE, "%s: workspace %zu < %zu", name, ws_bytes, (size_t)nblk * 2 * C * sizeof(float));
-  size_t smem = (size_t)kRedThreads * 2 * VEC * sizeof(float);
   float* part = reinterpret_cast<float*>(ws);
 #define LAUNCH(T, V) pdl(colreduce_kernel<T, V, F>, nblk, kRedThreads, smem, st)(f, (const T*)p0, (const T*)p1, M, C, tpr, part)
   if (dtype == MCG_F32) { if (VEC == 8) LAUNCH(float, 8); else LAUNCH(float, 1); }
@@ -165,22 +190,22 @@ static int launch_colreduce(F f, const void* p0, const void* p1, long long M, in
 }
 
 // One warp per channel: lanes stride over the per-block partials, then a shuffle tree (fixed order: deterministic).
+// Every lane issues ALL of its (at most 19 x 2) loads before the first add — the partials of one channel are 2*C floats
+// apart, so each load is its own L2 round trip and a dependent chain of them was 6-10 us per finalize (x 46 per step).
 __device__ __forceinline__ void warp_sum_partials(const float* partial, int nblk, int C, int c, double& s, double& q) {
   const int lane = threadIdx.x & 31;
-  double s0 = 0, s1 = 0, q0 = 0, q1 = 0;
-  int b = lane;
-  for (; b + 32 < nblk; b += 64) {  // two independent chains so the loads of consecutive iterations overlap
-    s0 += partial[(size_t)b * 2 * C + c];
-    q0 += partial[(size_t)b * 2 * C + C + c];
-    s1 += partial[(size_t)(b + 32) * 2 * C + c];
-    q1 += partial[(size_t)(b + 32) * 2 * C + C + c];
+  constexpr int kPer = (kRedMaxBlocks + 31) / 32;
+  float sv[kPer], qv[kPer];
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const int b = lane + 32 * i;
+    const bool ok = b < nblk;
+    sv[i] = ok ? partial[(size_t)b * 2 * C + c] : 0.f;
+    qv[i] = ok ? partial[(size_t)b * 2 * C + C + c] : 0.f;
   }
-  if (b < nblk) {
-    s0 += partial[(size_t)b * 2 * C + c];
-    q0 += partial[(size_t)b * 2 * C + C + c];
-  }
-  s = s0 + s1;
-  q = q0 + q1;
+  s = 0; q = 0;
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) { s += (double)sv[i]; q += (double)qv[i]; }
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
     q += __shfl_xor_sync(0xffffffffu, q, o);
@@ -233,8 +258,8 @@ __global__ void __launch_bounds__(256) sum2_finalize(const float* partial, int n
 // =====================================================================================================
 // VEC == 8 with FIXED: the launcher made (gridDim.x * 256) a multiple of C/8, so a thread keeps one channel group for all
 // of its rows: scale/shift live in registers and the row index advances without a division.
-template <typename TI, typename TO, int VEC, bool FIXED>
-__global__ void __launch_bounds__(256) affine_act_noise_kernel(
+template <typename TI, typename TO, int VEC, bool FIXED, int ACT = -1, bool NOISE = true>
+__global__ void __launch_bounds__(256, (FIXED && VEC == 8) ? MCG_AFF_MB : 1) affine_act_noise_kernel(
     const TI* __restrict__ y, long long M, int C, long long P, const float* __restrict__ scale,
     const float* __restrict__ shift, int act, float slope, float sigma, const float* __restrict__ noise,
     long long ns_n, long long ns_c, long long ns_p, const StepState* __restrict__ rng, int call_id,
@@ -252,18 +277,17 @@ __global__ void __launch_bounds__(256) affine_act_noise_kernel(
 #pragma unroll
     for (int i = 0; i < VEC; ++i) { sc[i] = scale[c0 + i]; sh[i] = shift[c0 + i]; }
   }
-  for (; idx < total; idx += stride) {
-    if (!FIXED) { m = idx / CG; c0 = (int)(idx % CG) * VEC; }
-    float v[VEC];
-    if (VEC == 8) ld8<TI>(y + m * C + c0, reinterpret_cast<float(&)[8]>(v));
-    else v[0] = ld<TI>(y, m * C + c0);
+  // one row: affine + activation + noise on 8 (or 1) loaded values, then the store
+  auto finish_row = [&](float (&v)[VEC], long long m, int c0, long long idx) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       float pre = v[i];
       if (scale) pre = FIXED ? sc[i] * v[i] + sh[i] : scale[c0 + i] * v[i] + shift[c0 + i];
-      v[i] = act_fwd(act, slope, pre);
+      v[i] = act_fwd(ACT >= 0 ? ACT : act, slope, pre);
     }
-    if (noise) {
+    if (!NOISE) {
+      // the generator's layers: no add_noise, and none of the Philox code's registers
+    } else if (noise) {
       long long n = m / P, p = m % P;
 #pragma unroll
       for (int i = 0; i < VEC; ++i) v[i] += sigma * noise[n * ns_n + (long long)(c0 + i) * ns_c + p * ns_p];
@@ -284,6 +308,28 @@ __global__ void __launch_bounds__(256) affine_act_noise_kernel(
     }
     if (VEC == 8) st8<TO>(out + m * C + c0, reinterpret_cast<const float(&)[8]>(v));
     else st<TO>(out, m * C + c0, v[0]);
+  };
+  if constexpr (FIXED && VEC == 8) {
+    // MCG_AFF_U rows of the thread's channel group per iteration, all loads issued before the first use
+    constexpr int U = MCG_AFF_U;
+    for (; idx + (U - 1) * stride < total; idx += U * stride, m += U * mstep) {
+      Raw8<TI> raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) raw[u] = ldraw8<TI>(y + (m + u * mstep) * C + c0);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float v[8];
+        unpack8(raw[u], v);
+        finish_row(v, m + u * mstep, c0, idx + u * stride);
+      }
+    }
+  }
+  for (; idx < total; idx += stride) {
+    if (!FIXED) { m = idx / CG; c0 = (int)(idx % CG) * VEC; }
+    float v[VEC];
+    if (VEC == 8) ld8<TI>(y + m * C + c0, reinterpret_cast<float(&)[8]>(v));
+    else v[0] = ld<TI>(y, m * C + c0);
+    finish_row(v, m, c0, idx);
     if (FIXED) m += mstep;
   }
 }
@@ -351,8 +397,8 @@ __global__ void __launch_bounds__(256) pack_elem_kernel(const TI* __restrict__ s
 // With BN:  gy = gamma*invstd*(g' - (xhat*dgamma + dbeta)/M) = A*(g' - ((y - mean)*B + D))  with per-channel A = gamma*invstd,
 // B = invstd*dgamma/M, D = dbeta/M.  FIXED (see affine_act_noise_kernel) keeps A, B, D, mean and the activation's
 // scale/shift in registers.
-template <typename TI, typename TO, int VEC, bool FIXED>
-__global__ void __launch_bounds__(256) act_bn_bwd_apply_kernel(
+template <typename TI, typename TO, int VEC, bool FIXED, int ACT = -1>
+__global__ void __launch_bounds__(256, (FIXED && VEC == 8 && ACT >= 0 && sizeof(TI) == 2) ? MCG_APP_MB : 1) act_bn_bwd_apply_kernel(
     const TI* __restrict__ g, const TI* __restrict__ y, long long M, int C, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ scale,
     const float* __restrict__ shift, int act, float slope, int use_output, const float* __restrict__ dgamma,
@@ -377,6 +423,47 @@ __global__ void __launch_bounds__(256) act_bn_bwd_apply_kernel(
       sc[i] = scale[c]; sh[i] = shift[c];
     }
   }
+  auto finish_row = [&](float (&gv)[VEC], const float (&yv)[VEC], long long m, int c0) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      int c = c0 + i;
+      if (mean) {
+        if (FIXED) {
+          float gp = gv[i] * act_grad(ACT >= 0 ? ACT : act, slope, sc[i] * yv[i] + sh[i], 0);
+          gv[i] = cA[i] * (gp - ((yv[i] - cM[i]) * cB[i] + cD[i]));
+        } else {
+          float pre = scale[c] * yv[i] + shift[c];
+          float gp = gv[i] * act_grad(ACT >= 0 ? ACT : act, slope, pre, 0);
+          float xh = (yv[i] - mean[c]) * invstd[c];
+          gv[i] = gamma[c] * invstd[c] * (gp - (xh * dgamma[c] + dbeta[c]) * inv_m);
+        }
+      } else {
+        gv[i] = gv[i] * act_grad(ACT >= 0 ? ACT : act, slope, yv[i], use_output);
+      }
+    }
+    if (VEC == 8) st8<TO>(gy + m * C + c0, reinterpret_cast<const float(&)[8]>(gv));
+    else st<TO>(gy, m * C + c0, gv[0]);
+  };
+  if constexpr (FIXED && VEC == 8) {
+    // MCG_APP_U rows per iteration: 2 x MCG_APP_U 16-byte (bf16) loads in flight per thread (the runtime-activation
+    // variant carries the switch's code and would spill with more than 2)
+    constexpr int U = ACT >= 0 ? MCG_APP_U : (MCG_APP_U < 2 ? MCG_APP_U : 2);
+    for (; idx + (U - 1) * stride < total; idx += U * stride, m += U * mstep) {
+      Raw8<TI> rg[U], ry[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        rg[u] = ldraw8<TI>(g + (m + u * mstep) * C + c0);
+        ry[u] = ldraw8<TI>(y + (m + u * mstep) * C + c0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float gv[8], yv[8];
+        unpack8(rg[u], gv);
+        unpack8(ry[u], yv);
+        finish_row(gv, yv, m + u * mstep, c0);
+      }
+    }
+  }
   for (; idx < total; idx += stride) {
     if (!FIXED) { m = idx / CG; c0 = (int)(idx % CG) * VEC; }
     float gv[VEC], yv[VEC];
@@ -387,25 +474,7 @@ __global__ void __launch_bounds__(256) act_bn_bwd_apply_kernel(
       gv[0] = ld<TI>(g, m * C + c0);
       yv[0] = ld<TI>(y, m * C + c0);
     }
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      int c = c0 + i;
-      if (mean) {
-        if (FIXED) {
-          float gp = gv[i] * act_grad(act, slope, sc[i] * yv[i] + sh[i], 0);
-          gv[i] = cA[i] * (gp - ((yv[i] - cM[i]) * cB[i] + cD[i]));
-        } else {
-          float pre = scale[c] * yv[i] + shift[c];
-          float gp = gv[i] * act_grad(act, slope, pre, 0);
-          float xh = (yv[i] - mean[c]) * invstd[c];
-          gv[i] = gamma[c] * invstd[c] * (gp - (xh * dgamma[c] + dbeta[c]) * inv_m);
-        }
-      } else {
-        gv[i] = gv[i] * act_grad(act, slope, yv[i], use_output);
-      }
-    }
-    if (VEC == 8) st8<TO>(gy + m * C + c0, reinterpret_cast<const float(&)[8]>(gv));
-    else st<TO>(gy, m * C + c0, gv[0]);
+    finish_row(gv, yv, m, c0);
     if (FIXED) m += mstep;
   }
 }
@@ -601,9 +670,14 @@ int mcg_act_bn_bwd_reduce(const void* g, const void* y, long long M, int C, int 
   if (!g || !y || !mean || !invstd || !scale || !shift || !dgamma || !dbeta)
     MCG_FAIL(MCG_ERR_SHAPE, "mcg_act_bn_bwd_reduce: null pointer");
   int nblk = 0;
-  BnBwdF f{mean, invstd, scale, shift, act, slope};
-  int rc = launch_colreduce(f, g, y, M, C, dtype, workspace, workspace_bytes, as_stream(stream), &nblk,
-                            "mcg_act_bn_bwd_reduce");
+  int rc;
+#define MCG_RED(A) rc = launch_colreduce(BnBwdF<A>{mean, invstd, scale, shift, act, slope}, g, y, M, C, dtype, workspace, \
+                                         workspace_bytes, as_stream(stream), &nblk, "mcg_act_bn_bwd_reduce")
+  if (C % 8) MCG_RED(-1);
+  else if (act == MCG_ACT_RELU) MCG_RED(MCG_ACT_RELU);
+  else if (act == MCG_ACT_LRELU) MCG_RED(MCG_ACT_LRELU);
+  else MCG_RED(-1);
+#undef MCG_RED
   if (rc) return rc;
   // partial[.,0,:] = sum g' -> dbeta ; partial[.,1,:] = sum g' xhat -> dgamma; acc_* are the parameter
   // gradients, which accumulate across the real and fake calls of one pass as in Chainer.
@@ -632,10 +706,23 @@ int mcg_affine_act_noise(const void* y, long long M, int C, long long P, int dty
   dispatch2(dtype, out_dtype, [&](auto ti, auto to) {
     using TI = decltype(ti);
     using TO = decltype(to);
-    if (C % 8 == 0 && 256 % (C / 8) == 0)   // a thread keeps its channel group: per-channel constants in registers
-      pdl(affine_act_noise_kernel<TI, TO, 8, true>, grid_for(M * (C / 8)), 256, 0, st)(
-          (const TI*)y, M, C, P, scale, shift, act, slope, sigma, noise, ns_n, ns_c, ns_p, rng, call_id, (TO*)out);
-    else if (C % 8 == 0)
+    if (C % 8 == 0 && 256 % (C / 8) == 0) {  // a thread keeps its channel group: per-channel constants in registers
+      const bool has_noise = noise || (rng && sigma != 0.f);
+#define MCG_AFF(A)                                                                                                  \
+  do {                                                                                                              \
+    if (has_noise)                                                                                                  \
+      pdl(affine_act_noise_kernel<TI, TO, 8, true, A, true>, grid_for(M * (C / 8)), 256, 0, st)(                   \
+          (const TI*)y, M, C, P, scale, shift, act, slope, sigma, noise, ns_n, ns_c, ns_p, rng, call_id, (TO*)out); \
+    else                                                                                                            \
+      pdl(affine_act_noise_kernel<TI, TO, 8, true, A, false>, grid_for(M * (C / 8)), 256, 0, st)(                  \
+          (const TI*)y, M, C, P, scale, shift, act, slope, sigma, noise, ns_n, ns_c, ns_p, rng, call_id, (TO*)out); \
+  } while (0)
+      if (act == MCG_ACT_RELU) MCG_AFF(MCG_ACT_RELU);
+      else if (act == MCG_ACT_LRELU) MCG_AFF(MCG_ACT_LRELU);
+      else if (act == MCG_ACT_TANH) MCG_AFF(MCG_ACT_TANH);
+      else MCG_AFF(MCG_ACT_NONE);
+#undef MCG_AFF
+    } else if (C % 8 == 0)
       pdl(affine_act_noise_kernel<TI, TO, 8, false>, grid_for(M * (C / 8)), 256, 0, st)(
           (const TI*)y, M, C, P, scale, shift, act, slope, sigma, noise, ns_n, ns_c, ns_p, rng, call_id, (TO*)out);
     else
@@ -700,11 +787,16 @@ int mcg_act_bn_bwd_apply(const void* g, const void* y, long long M, int C, int d
   dispatch2(dtype, out_dtype, [&](auto ti, auto to) {
     using TI = decltype(ti);
     using TO = decltype(to);
-    if (C % 8 == 0 && 256 % (C / 8) == 0)
-      pdl(act_bn_bwd_apply_kernel<TI, TO, 8, true>, grid_for(M * (C / 8)), 256, 0, st)(
-          (const TI*)g, (const TI*)y, M, C, mean, invstd, gamma, scale, shift, act, slope, use_output, dgamma, dbeta,
-          inv_m, (TO*)gy);
-    else if (C % 8 == 0)
+    if (C % 8 == 0 && 256 % (C / 8) == 0) {
+#define MCG_APP(A)                                                                                                \
+  pdl(act_bn_bwd_apply_kernel<TI, TO, 8, true, A>, grid_for(M * (C / 8)), 256, 0, st)(                           \
+      (const TI*)g, (const TI*)y, M, C, mean, invstd, gamma, scale, shift, act, slope, use_output, dgamma, dbeta, \
+      inv_m, (TO*)gy)
+      if (act == MCG_ACT_RELU) MCG_APP(MCG_ACT_RELU);
+      else if (act == MCG_ACT_LRELU) MCG_APP(MCG_ACT_LRELU);
+      else MCG_APP(-1);
+#undef MCG_APP
+    } else if (C % 8 == 0)
       pdl(act_bn_bwd_apply_kernel<TI, TO, 8, false>, grid_for(M * (C / 8)), 256, 0, st)(
           (const TI*)g, (const TI*)y, M, C, mean, invstd, gamma, scale, shift, act, slope, use_output, dgamma, dbeta,
           inv_m, (TO*)gy);

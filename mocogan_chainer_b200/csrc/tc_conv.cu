@@ -25,6 +25,9 @@
 namespace mcg {
 
 enum { kFprop = 0, kDgrad = 1, kWgrad = 2 };
+#ifndef MCG_TC_DYN_DEFAULT
+#define MCG_TC_DYN_DEFAULT 0
+#endif
 
 struct TcTap {
   int16_t dw, dh, dt, kidx;  // A-box coordinate offsets; kidx = linear tap index (kt,kh,kw)
@@ -48,6 +51,7 @@ struct TcParams {
   // cut between CTAs (stream-K) meets again in the fp32 red.add of the epilogue.
   int nboxes, ntn, ntiles;
   long long total_units, units_per_cta;
+  int dyn, sched_slot;   // dynamic work distribution (fprop/dgrad): counter slot in g_tc_sched_ctr; 0 = static ranges
   int total_boxes;                                            // wgrad: K steps per tile
   int total_slabs, kreal;                                     // wgrad: valid 64-row slabs; real row length of dw
   int wrows;                                                  // real rows of w / dw (< Cout when the channels were padded)
@@ -78,11 +82,13 @@ struct TcSeg {
 template <int MODE, int MT>
 struct TcSegIter {
   long long u, u_end;
+  __device__ __forceinline__ TcSegIter() : u(0), u_end(0) {}
   __device__ __forceinline__ explicit TcSegIter(const TcParams& P) {
     u = (long long)blockIdx.x * P.units_per_cta;
     u_end = u + P.units_per_cta;
     if (u_end > P.total_units) u_end = P.total_units;
   }
+  __device__ __forceinline__ void set(long long a, long long b) { u = a; u_end = b; }
   __device__ __forceinline__ bool next(const TcParams& P, TcSeg& s) {
     if (u >= u_end) return false;
     if (MODE == kWgrad) {
@@ -108,6 +114,56 @@ struct TcSegIter {
   }
 };
 
+// ---- dynamic work distribution -------------------------------------------------------------------------------
+// A static one-range-per-CTA split assumes all CTAs of the grid start together.  They do not when another stream's
+// kernel (a small-grid convolution, a collective) holds some SMs: the CTAs that start late finish late and the whole
+// kernel takes up to twice as long.  With P.dyn the CTAs of a fprop/dgrad launch instead DRAW ranges of units from a
+// global counter (guided self-scheduling: remaining / (2 x grid), never less than one tile step), so a late CTA simply
+// draws less.  The producer thread draws (one range ahead, so the atomic's latency hides under the loads of the current
+// range) and publishes each range to the MMA and epilogue roles through a small shared-memory ring.
+constexpr int kSchedDepth = 8;
+constexpr int kSchedSlots = 1024;
+__device__ int g_tc_sched_ctr[kSchedSlots];    // units handed out so far; the last CTA to leave resets its slot
+__device__ int g_tc_sched_done[kSchedSlots];
+struct TcSchedSmem {
+  int u0[kSchedDepth], n[kSchedDepth];
+  int first_u0;                                // drawn by thread 0 on kernel entry, under the prologue
+};
+__device__ __forceinline__ int tc_sched_chunk(int total, int handed_out, int mt) {
+  int rem = total - handed_out;
+  if (rem < 0) rem = 0;
+  int c = rem / (2 * (int)gridDim.x);
+  c -= c % mt;
+  return c < mt ? mt : c;
+}
+// Consumer side (MMA issuer, epilogue threads); in static mode: the CTA's one range, no shared-memory traffic.
+struct TcRanges {
+  uint32_t full_a, empty_a;
+  const TcSchedSmem* sm;
+  int slot;
+  uint32_t ph;
+  bool dyn, done;
+  __device__ __forceinline__ TcRanges(const TcParams& P, const TcSchedSmem* sm_, uint32_t full, uint32_t empty)
+      : full_a(full), empty_a(empty), sm(sm_), slot(0), ph(0), dyn(P.dyn != 0), done(false) {}
+  __device__ __forceinline__ bool next(const TcParams& P, long long& u, long long& u_end, int* err) {
+    if (!dyn) {
+      if (done) return false;
+      done = true;
+      u = (long long)blockIdx.x * P.units_per_cta;
+      u_end = u + P.units_per_cta;
+      if (u_end > P.total_units) u_end = P.total_units;
+      return u < u_end;
+    }
+    if (!mbar_wait_a(full_a + slot * 8, ph, err)) return false;
+    const int a = *(volatile const int*)&sm->u0[slot], c = *(volatile const int*)&sm->n[slot];
+    mbar_arrive_a(empty_a + slot * 8);
+    if (++slot == kSchedDepth) { slot = 0; ph ^= 1; }
+    if (c <= 0) return false;
+    u = a; u_end = (long long)a + c;
+    return true;
+  }
+};
+
 struct TcBox { int w0, h0, t0, n0; };
 __device__ __forceinline__ TcBox tc_decode_box(const TcParams& P, int bi) {
   TcBox b;
@@ -124,20 +180,25 @@ __device__ __forceinline__ TcBox tc_decode_box(const TcParams& P, int bi) {
 // warps share each TMEM lane quarter and take alternate 32-column chunks.
 template <int MODE, int BN, int MT, int NBUF>
 __device__ __forceinline__ void tc_epilogue_role(const TcParams& P, void* __restrict__ out, const float* __restrict__ bias,
-                                                 uint32_t tmem, uint32_t tfull_a, uint32_t tempty_a, int warp, int lane, int* err) {
+                                                 uint32_t tmem, uint32_t tfull_a, uint32_t tempty_a, int warp, int lane, int* err,
+                                                 TcRanges rng) {
   constexpr int ACC_COLS = MT * BN;
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // accumulator row == TMEM lane
-    TcSegIter<MODE, MT> iter(P);
+    TcSegIter<MODE, MT> iter;
     TcSeg sg;
     uint32_t seg = 0;
+    long long ru, ru_end;
+    bool alive = true;
+    while (alive && rng.next(P, ru, ru_end, err)) {
+    iter.set(ru, ru_end);
     while (iter.next(P, sg)) {
       const int nt = sg.tile % P.ntn, mg = sg.tile / P.ntn;
       const int ncol0 = nt * BN;
       const bool have_acc = sg.nk > 0;
       const uint32_t buf = seg % NBUF;
       if (have_acc) {
-        if (!mbar_wait_a(tfull_a + buf * 8, (seg / NBUF) & 1, err)) break;
+        if (!mbar_wait_a(tfull_a + buf * 8, (seg / NBUF) & 1, err)) { alive = false; break; }
         tc_fence_after();
       }
       const uint32_t acc = tmem + (uint32_t(q * 32) << 16) + buf * ACC_COLS;
@@ -241,6 +302,7 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& P, void* __rest
         ++seg;
       }
     }
+    }
 }
 
 template <int MODE, int BN, int MT, int STAGES>
@@ -258,13 +320,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint64_t sfull_bar[kSchedDepth], sempty_bar[kSchedDepth];
+  __shared__ TcSchedSmem sched;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* err = &g_tc_error;
 
   if (threadIdx.x == 0) {
+    // the CTA's first range is drawn here, so the atomic's round trip hides under the rest of the prologue
+    if (P.dyn) sched.first_u0 = atomicAdd(&g_tc_sched_ctr[P.sched_slot], tc_sched_chunk((int)P.total_units, 0, MT));
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiThreads); }
+    for (int i = 0; i < kSchedDepth; ++i) { mbar_init(&sfull_bar[i], 1); mbar_init(&sempty_bar[i], 1 + kEpiThreads); }
     fence_barrier_init();
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
@@ -279,6 +346,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
   const uint32_t smem_a = smem_u32(smem);
   const uint32_t full_a = smem_u32(&full_bar[0]), empty_a = smem_u32(&empty_bar[0]);
   const uint32_t tfull_a = smem_u32(&tfull_bar[0]), tempty_a = smem_u32(&tempty_bar[0]);
+  const uint32_t sfull_a = smem_u32(&sfull_bar[0]), sempty_a = smem_u32(&sempty_bar[0]);
 
   if (warp == 0) {
     // ================================================= TMA producer =========================================
@@ -286,12 +354,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     // tap / slab decode hoisted, barrier and stage addresses advanced incrementally.
     if (elect_one()) {
       const uint64_t map_a = reinterpret_cast<uint64_t>(&mapA), map_b = reinterpret_cast<uint64_t>(&mapB);
-      TcSegIter<MODE, MT> iter(P);
+      TcSegIter<MODE, MT> iter;
       TcSeg sg;
       int s = 0;
       uint32_t ph = 1;   // ring slot and the parity its `empty` barrier is waited with
       uint32_t stage_a = smem_a, full_s = full_a, empty_s = empty_a;
       bool alive = true;
+      // work ranges: static = the CTA's one range; dynamic = drawn from the launch's counter, one range ahead
+      const int total = (int)P.total_units;
+      int cur_u0 = 0, cur_c = 0, nxt_u0 = 0, nxt_c = 0, pslot = 0;
+      uint32_t pph = 1;
+      bool static_done = false;
+      if (P.dyn) { nxt_c = tc_sched_chunk(total, 0, MT); nxt_u0 = *(volatile int*)&sched.first_u0; }
+      for (;;) {
+        if (!alive) break;
+        if (P.dyn) {
+          cur_u0 = nxt_u0; cur_c = nxt_c;
+          int n = total - cur_u0;
+          if (n > cur_c) n = cur_c;
+          if (n < 0) n = 0;
+          if (!mbar_wait_a(sempty_a + pslot * 8, pph, err)) break;
+          sched.u0[pslot] = cur_u0; sched.n[pslot] = n;
+          mbar_arrive_a(sfull_a + pslot * 8);          // release: the two stores above are visible to the waiters
+          if (++pslot == kSchedDepth) { pslot = 0; pph ^= 1; }
+          if (n == 0) break;
+          nxt_c = tc_sched_chunk(total, cur_u0 + cur_c, MT);
+          nxt_u0 = atomicAdd(&g_tc_sched_ctr[P.sched_slot], nxt_c);   // consumed when this range's loads are issued
+          iter.set(cur_u0, (long long)cur_u0 + n);
+        } else {
+          if (static_done) break;
+          static_done = true;
+          iter = TcSegIter<MODE, MT>(P);
+        }
       while (alive && iter.next(P, sg)) {
         const int nt = sg.tile % P.ntn, mg = sg.tile / P.ntn;
         const int ncol0 = nt * BN;
@@ -366,6 +460,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
           }
         }
       }
+      }
     }
   } else if (warp == 1) {
     // ================================================= MMA issuer ===========================================
@@ -375,16 +470,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
       const uint32_t idesc = make_idesc_bf16(128, BN, A_MN, B_MN);
       const uint32_t desc_hi = smem_desc_hi(1024);
       const uint32_t a_lo0 = smem_desc_lo(smem_a, A_MN ? 8192 : 16), b_lo0 = smem_desc_lo(smem_a + MT * A_BYTES, B_MN ? 8192 : 16);
-      TcSegIter<MODE, MT> iter(P);
+      TcSegIter<MODE, MT> iter;
+      TcRanges rng(P, &sched, sfull_a, sempty_a);
       TcSeg sg;
       uint32_t seg = 0, ph = 0;
       int s = 0;
       uint32_t a_lo = a_lo0, b_lo = b_lo0, full_s = full_a, empty_s = empty_a;
       bool alive = true;
+      long long ru, ru_end;
+      while (alive && rng.next(P, ru, ru_end, err)) {
+      iter.set(ru, ru_end);
       while (alive && iter.next(P, sg)) {
         if (sg.nk == 0) continue;
         const uint32_t buf = seg % NBUF;
-        if (!mbar_wait_a(tempty_a + buf * 8, ((seg / NBUF) & 1) ^ 1, err)) break;
+        if (!mbar_wait_a(tempty_a + buf * 8, ((seg / NBUF) & 1) ^ 1, err)) { alive = false; break; }
         tc_fence_after();
         const uint32_t acc = tmem + buf * ACC_COLS;
         const int nlive = sg.nlive;
@@ -406,14 +505,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
         if (alive) umma_commit_a(tfull_a + buf * 8);
         ++seg;
       }
+      }
     }
   } else {
     // ================================================= epilogue ============================================
-    tc_epilogue_role<MODE, BN, MT, NBUF>(P, out, bias, tmem, tfull_a, tempty_a, warp, lane, err);
+    tc_epilogue_role<MODE, BN, MT, NBUF>(P, out, bias, tmem, tfull_a, tempty_a, warp, lane, err,
+                                         TcRanges(P, &sched, sfull_a, sempty_a));
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+  if (P.dyn && threadIdx.x == 0) {
+    // every draw of this CTA has returned; the last CTA to leave hands the counter slot back zeroed (the next launch
+    // that uses the slot — the same graph node one replay later — is ordered after this kernel)
+    __threadfence();
+    if (atomicAdd(&g_tc_sched_done[P.sched_slot], 1) == (int)gridDim.x - 1) {
+      g_tc_sched_ctr[P.sched_slot] = 0;
+      g_tc_sched_done[P.sched_slot] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // =============================================================================================================
@@ -570,7 +681,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_tr_kernel(const __grid_
     }
   } else {
     // ================================================= epilogue ============================================
-    tc_epilogue_role<MODE, BN, MT, NBUF>(P, out, bias, tmem, tfull_a, tempty_a, warp, lane, err);
+    tc_epilogue_role<MODE, BN, MT, NBUF>(P, out, bias, tmem, tfull_a, tempty_a, warp, lane, err,
+                                         TcRanges(P, nullptr, 0, 0));   // P.dyn == 0 here: static ranges
   }
   tc_fence_before();
   __syncthreads();
@@ -731,6 +843,24 @@ static int split_units(TcParams& P, long long units, long long min_per_cta) {
   return (int)((units + P.units_per_cta - 1) / P.units_per_cta);
 }
 
+// Dynamic work distribution is worth its two atomics per range only when a CTA has several tile steps to draw from.
+static std::atomic<int> g_tc_dyn{-1};
+static std::atomic<unsigned> g_tc_sched_seq{0};
+static void tc_set_schedule(TcParams& P, int mode, int grid, int mt) {
+  int dyn = g_tc_dyn.load(std::memory_order_relaxed);
+  if (dyn < 0) {
+    const char* e = getenv("MCG_TC_DYN");
+    dyn = e ? atoi(e) : MCG_TC_DYN_DEFAULT;
+    g_tc_dyn.store(dyn, std::memory_order_relaxed);
+  }
+  P.dyn = 0;
+  P.sched_slot = 0;
+  if (dyn && mode != kWgrad && P.total_units < (1LL << 30) && P.total_units >= 4LL * grid * mt) {
+    P.dyn = 1;
+    P.sched_slot = (int)(g_tc_sched_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
+  }
+}
+
 template <int MODE, int BN, int MT>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, int grid, void* out, const float* bias,
                      cudaStream_t st, const char* who) {
@@ -750,8 +880,9 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
   return 0;
 }
 template <int MODE>
-static int launch_tc_cfg(TileCfg c, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, int grid, void* out,
+static int launch_tc_cfg(TileCfg c, const CUtensorMap& ma, const CUtensorMap& mb, TcParams& P, int grid, void* out,
                          const float* bias, cudaStream_t st, const char* who) {
+  tc_set_schedule(P, MODE, grid, c.mt);
 #define MCG_TC_CASE(bn_, mt_) \
   if (c.bn == bn_ && c.mt == mt_) return launch_tc<MODE, bn_, mt_>(ma, mb, P, grid, out, bias, st, who)
   MCG_TC_CASE(64, 1); MCG_TC_CASE(64, 2);
