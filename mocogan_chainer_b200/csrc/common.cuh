@@ -158,7 +158,13 @@ __device__ __forceinline__ void unpack8(const Raw8<__nv_bfloat16>& r, float (&v)
 // (many rows in flight, 128 registers) is not the fastest inside the 4-stream step: its blocks must fit beside a
 // persistent convolution CTA (38 K of the SM's 64 K registers), so the register cap matters more than the unroll.
 #ifndef MCG_RED_U
-#define MCG_RED_U 4
+#define MCG_RED_U 4      // one-tensor reductions (statistics, bias gradients)
+#endif
+#ifndef MCG_RED_U2
+#define MCG_RED_U2 2     // two-tensor reductions (BatchNorm backward sums)
+#endif
+#ifndef MCG_RED_MB
+#define MCG_RED_MB 3     // ncu: at 85-89 registers the BatchNorm-backward reduction fitted only 2 blocks per SM
 #endif
 #ifndef MCG_AFF_U
 #define MCG_AFF_U 1

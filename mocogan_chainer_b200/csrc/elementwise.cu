@@ -88,7 +88,7 @@ struct BnBwdF {  // sum g', sum g'*xhat with g' = g * act'(scale*y+shift)
 };
 
 template <typename T, int VEC, typename F>
-__global__ void __launch_bounds__(kRedThreads) colreduce_kernel(F f, const T* p0, const T* p1, long long M, int C,
+__global__ void __launch_bounds__(kRedThreads, F::kTwo ? MCG_RED_MB : 4) colreduce_kernel(F f, const T* p0, const T* p1, long long M, int C,
                                                                int tpr, float* __restrict__ partial) {
   pdl_enter();
   extern __shared__ float red[];  // [rpb][tpr][2*VEC]
@@ -101,18 +101,21 @@ __global__ void __launch_bounds__(kRedThreads) colreduce_kernel(F f, const T* p0
   if (tx < CG) {
     typename F::template Regs<VEC> regs;
     f.template prep<VEC>(tx * VEC, regs);
-    const long long step = (long long)gridDim.x * rpb;
-    long long m = (long long)blockIdx.x * rpb + ty;
     const long long col = (long long)tx * VEC;
+    // A block walks the matrix in TILES of U x rpb consecutive rows (one contiguous span of memory per tensor), U rows per
+    // thread with all loads issued before the first use.  Rows of one thread that are a whole grid apart (the first
+    // version) kept as many bytes in flight but opened U DRAM pages at once and ran slower than U = 1.
+    constexpr int U = (VEC == 8) ? (F::kTwo ? (sizeof(T) == 4 ? 1 : MCG_RED_U2) : MCG_RED_U) : 1;
+    const long long tile = (long long)rpb * U;
+    long long base = (long long)blockIdx.x * tile;
     if constexpr (VEC == 8) {
-      // MCG_RED_U rows per iteration: all loads first (raw, 16-32 B each), arithmetic afterwards
-      constexpr int U = MCG_RED_U;
-      for (; m + (U - 1) * step < M; m += U * step) {
+      for (; base + tile <= M; base += (long long)gridDim.x * tile) {
         Raw8<T> r0[U], r1[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          r0[u] = ldraw8<T>(p0 + (m + u * step) * C + col);
-          if (F::kTwo) r1[u] = ldraw8<T>(p1 + (m + u * step) * C + col);
+          const long long m = base + (long long)u * rpb + ty;
+          r0[u] = ldraw8<T>(p0 + m * C + col);
+          if (F::kTwo) r1[u] = ldraw8<T>(p1 + m * C + col);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -123,16 +126,21 @@ __global__ void __launch_bounds__(kRedThreads) colreduce_kernel(F f, const T* p0
         }
       }
     }
-    for (; m < M; m += step) {
-      float v0[VEC], v1[VEC];
-      if (VEC == 8) {
-        ld8<T>(p0 + m * C + col, reinterpret_cast<float(&)[8]>(v0));
-        if (F::kTwo) ld8<T>(p1 + m * C + col, reinterpret_cast<float(&)[8]>(v1));
-      } else {
-        v0[0] = ld<T>(p0, m * C + col);
-        if (F::kTwo) v1[0] = ld<T>(p1, m * C + col);
+    // the last, partial tile of the matrix (and everything when VEC == 1): row by row
+    for (; base < M; base += (long long)gridDim.x * tile) {
+      for (int u = 0; u < U; ++u) {
+        const long long m = base + (long long)u * rpb + ty;
+        if (m >= M) break;
+        float v0[VEC], v1[VEC];
+        if (VEC == 8) {
+          ld8<T>(p0 + m * C + col, reinterpret_cast<float(&)[8]>(v0));
+          if (F::kTwo) ld8<T>(p1 + m * C + col, reinterpret_cast<float(&)[8]>(v1));
+        } else {
+          v0[0] = ld<T>(p0, m * C + col);
+          if (F::kTwo) v1[0] = ld<T>(p1, m * C + col);
+        }
+        f.template acc<VEC>(v0, v1, regs, a, b);
       }
-      f.template acc<VEC>(v0, v1, regs, a, b);
     }
   }
   float* mine = red + ((size_t)ty * tpr + tx) * 2 * VEC;
