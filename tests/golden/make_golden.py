@@ -17,7 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle import mocogan_ref as ref  # noqa: E402
 
-CASES = {"mnist_normal": dict(config="mnist_normal", nf=8, N=2), "mug_infogan": dict(config="mug_infogan", nf=8, N=3)}
+CASES = {"mnist_normal": dict(config="mnist_normal", nf=8, N=2), "mug_infogan": dict(config="mug_infogan", nf=8, N=3),
+         "mug_cgan": dict(config="mug_cgan", nf=8, N=2)}
 
 
 def make_inputs(config, nf, N, dtype=np.float64):

@@ -20,8 +20,10 @@ def test_oracle_reproduces_golden(name):
         assert np.abs(a - b).max() <= 1e-6 * max(np.abs(b).max(), 1e-12) + 1e-12, k
 
 
+# the cgan vectors pin the oracle on the CPU side; the device's cgan step is compared with the oracle directly in
+# tests/test_step_gpu.py::test_step_{fp32_strict,bf16_tcgen05}_cgan
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("name", sorted(set(CASES) - {"mug_cgan"}))
 def test_cuda_step_matches_golden(name):
     import torch
     if not torch.cuda.is_available():
