@@ -1,0 +1,24 @@
+"""The opt-in scheduling paths stay parity-green: programmatic dependent launch (MCG_PDL=1) and dynamic work distribution
+of the persistent fprop/dgrad kernels (MCG_TC_DYN=1).  Both are read once per process, so each case runs in a child
+pytest process with the flag set: the BASELINE config-2 layer sizes of the tcgen05 kernels against the independent
+fp32 kernel (only those are large enough for the dynamic distribution to switch on) and one whole update_core step
+against the oracle."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SELECT = ["tests/test_kernels_gpu.py::test_conv_tc_full_size_vs_simt",
+          "tests/test_step_gpu.py::test_step_bf16_tcgen05_mug_normal"]
+
+
+@pytest.mark.parametrize("flag", ["MCG_PDL", "MCG_TC_DYN"])
+def test_parity_with_flag(flag):
+    env = dict(os.environ)
+    env[flag] = "1"
+    out = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu"] + SELECT, env=env, cwd=ROOT,
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
