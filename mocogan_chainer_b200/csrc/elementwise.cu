@@ -174,13 +174,20 @@ static int launch_colreduce(F f, const void* p0, const void* p1, long long M, in
   // 85 registers, 4 for the statistics) — 592 blocks of a 3-per-SM kernel ran as a full wave plus a third of one
   int cap = kRedMaxBlocks;
   {
-    int per_sm = 0;
-    cudaError_t e = cudaSuccess;
-    if (dtype == MCG_F32) e = VEC == 8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<float, 8, F>, kRedThreads, smem)
-                                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<float, 1, F>, kRedThreads, smem);
-    else e = VEC == 8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<__nv_bfloat16, 8, F>, kRedThreads, smem)
-                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<__nv_bfloat16, 1, F>, kRedThreads, smem);
-    if (e == cudaSuccess && per_sm > 0 && per_sm * num_sms() < cap) cap = per_sm * num_sms();
+    static std::atomic<int> cached[2][2];      // [dtype][VEC == 8] -> resident blocks per SM (+1; 0 = not asked yet)
+    std::atomic<int>& slot = cached[dtype == MCG_F32 ? 0 : 1][VEC == 8 ? 1 : 0];
+    int per_sm = slot.load(std::memory_order_relaxed) - 1;
+    if (per_sm < 0) {
+      per_sm = 0;
+      cudaError_t e = cudaSuccess;
+      if (dtype == MCG_F32) e = VEC == 8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<float, 8, F>, kRedThreads, smem)
+                                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<float, 1, F>, kRedThreads, smem);
+      else e = VEC == 8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<__nv_bfloat16, 8, F>, kRedThreads, smem)
+                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<__nv_bfloat16, 1, F>, kRedThreads, smem);
+      if (e != cudaSuccess) { per_sm = 0; (void)cudaGetLastError(); }
+      slot.store(per_sm + 1, std::memory_order_relaxed);
+    }
+    if (per_sm > 0 && per_sm * num_sms() < cap) cap = per_sm * num_sms();
   }
   int nblk = (int)(want < cap ? want : cap);
   if (nblk < 1) nblk = 1;
