@@ -1,5 +1,7 @@
 #!/bin/bash
 # A/B of programmatic dependent launch on one GPU: parity first (MCG_PDL=1 through the whole-step tests), then bench lines.
+# libmcg_ew.so = the variant whose streaming kernels also release their successor early; build it first with
+#   MCG_LIB_OUT=$PWD/mocogan_chainer_b200/libmcg_ew.so MCG_OBJ_TAG=obj_ew MCG_EXTRA_FLAGS=-DMCG_PDL_EW_TRIGGER=1 tools/build_lib.sh
 mkdir -p gpurun_out
 B="--steps 60 --warmup 10 --no-cpu-baseline"
 MCG_PDL=1 timeout 300 python -m pytest tests/test_step_gpu.py tests/test_surface_gpu.py -m gpu -x -q > gpurun_out/tests_pdl1.log 2>&1; echo "pdl1 tests rc=$? $(tail -1 gpurun_out/tests_pdl1.log)"
