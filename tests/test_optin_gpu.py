@@ -11,14 +11,19 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SELECT = ["tests/test_kernels_gpu.py::test_conv_tc_full_size_vs_simt",
-          "tests/test_step_gpu.py::test_step_bf16_tcgen05_mug_normal"]
+STEP = ["tests/test_step_gpu.py::test_step_bf16_tcgen05_mug_normal"]
+SELECT = {
+    # every kernel of a step launched with the programmatic-serialization attribute, eager and multi-stream
+    "MCG_PDL": STEP + ["tests/test_step_gpu.py::test_step_fp32_strict_infogan"],
+    # the dynamic distribution only switches on when a CTA has >= 4 tile steps: the full-size layers
+    "MCG_TC_DYN": ["tests/test_kernels_gpu.py::test_conv_tc_full_size_vs_simt"] + STEP,
+}
 
 
-@pytest.mark.parametrize("flag", ["MCG_PDL", "MCG_TC_DYN"])
+@pytest.mark.parametrize("flag", sorted(SELECT))
 def test_parity_with_flag(flag):
     env = dict(os.environ)
     env[flag] = "1"
-    out = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu"] + SELECT, env=env, cwd=ROOT,
+    out = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu"] + SELECT[flag], env=env, cwd=ROOT,
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
