@@ -163,13 +163,32 @@ def build_updater(batch, seed, use_graph, model="normal"):
     return up, it
 
 
+def csrc_sha():
+    """sha256 over the CUDA sources libmcg.so is built from: ties committed ncu figures to the build they came from."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "mocogan_chainer_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
 def load_traffic():
-    """Measured DRAM bytes per launch (ncu --set full) of the kernels profiled under profiles/, keyed kernel:layer."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(p):
-        with open(p) as f:
-            return json.load(f)
-    return {}
+    """Measured DRAM bytes per launch (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum) of the kernels
+    profiled under profiles/, keyed kernel:layer, together with the csrc sha of the build that was profiled.  A file
+    whose sha differs from the sources in the tree is stale: its figures are NOT reported (traffic = null)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            with open(p) as f:
+                d = json.load(f)
+            sha = d.get("csrc_sha")
+            if sha is not None and sha == csrc_sha():
+                return d, name
+            return {"stale": True, "csrc_sha": sha}, name
+    return {}, None
 
 
 def time_conv_layers(K, torch, peaks):
@@ -278,43 +297,118 @@ def time_stream_kernels(K, torch, peaks):
     return rows
 
 
-def gen_frames_per_s(torch, peaks, batch=256, video_len=32, iters=8):
-    """BASELINE config 5 (generate_samples inference): generator only, batch 256 clips of 32 frames, BatchNorm in
-    batch-statistics mode as generate_samples.py runs it, plus the uint8 / grid post-processing.  64x64 frames: the
-    reference's generator cannot emit 128x128 (net.py:115 hard-codes 64, 64)."""
+GEN_GF_PER_FRAME = 116.82 / 560.0     # generator forward 116.82 GF for 560 frames of 64x64
+
+
+def gen_frames_per_s(torch, peaks, rank, world, barrier, batch=256, video_len=32, iters=8, size=64):
+    """BASELINE config 5 (generate_samples inference): generator only, batch 256 clips of 32 frames PER GPU, BatchNorm
+    in batch-statistics mode as generate_samples.py runs it, plus the uint8 / grid post-processing; the whole batch is
+    one CUDA-graph replay.  size=64 is the reference's generator (net.py:115 hard-codes 64, 64; SURVEY.md §8d config 5);
+    size=128 is the labelled extension (model/net128.py: one more deconvolution stage, parity unpinned)."""
     from mocogan_chainer_b200 import chainer, generate_samples
     from mocogan_chainer_b200 import random as mrandom
-    from mocogan_chainer_b200.model.net import ImageGenerator
     chainer.config.compute_dtype = "bf16"
     np.random.seed(0)
-    G = ImageGenerator(50, 10, 6, 3, 64, video_len)
+    if size == 64:
+        from mocogan_chainer_b200.model.net import ImageGenerator
+        G = ImageGenerator(50, 10, 6, 3, 64, video_len)
+        gf_per_frame = GEN_GF_PER_FRAME
+    else:
+        from mocogan_chainer_b200.model.net128 import ImageGenerator128
+        G = ImageGenerator128(50, 10, 6, 3, 64, video_len)
+        gf_per_frame = G.forward_gflop_per_frame()
     G.arena()
-    mrandom.set_source(mrandom.DeviceRandom(seed=99, device="cuda", video_length=video_len))
-    src = mrandom.get_source()
+    src = mrandom.set_source(mrandom.DeviceRandom(seed=99 + rank, device="cuda", video_length=video_len))
+    out = {}
 
     def once():
         src.begin_step()
-        return generate_samples.generate(G, batch, grid=True)
+        out["u8"], out["grid"] = generate_samples.generate(G, batch, grid=True)
 
     torch.cuda.empty_cache()      # the training legs before this one leave multi-GB caches and graph pools behind
-    for _ in range(4):
+    for _ in range(3):
         once()
     torch.cuda.synchronize()
+    graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            once()
+        graph = g
+    except Exception as e:   # noqa: BLE001 — an uncapturable generator is reported (cuda_graph: false), not hidden
+        sys.stderr.write("gen: CUDA-graph capture failed (%s); timing eager launches\n" % (e,))
+        torch.cuda.synchronize()
+    run = graph.replay if graph is not None else once
+    for _ in range(3):
+        run()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        u8, grid = once()
+        run()
     e1.record()
-    torch.cuda.synchronize()
+    barrier()
     ms = e0.elapsed_time(e1) / iters
-    frames = batch * video_len
-    gflop_per_frame = 116.82 / 560.0     # SURVEY.md App. C: generator forward 116.82 GF for 560 frames
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt[0])
+    assert int(out["u8"].max()) > 0
+    frames = batch * video_len * world
     return {"metric": "generator frames/s (generate_samples path: G forward + uint8/grid post-processing)",
-            "value": frames / ms * 1e3, "unit": "frames/s", "ms_per_batch": ms,
-            "config": {"workload": "BASELINE config 5 at the reference's native 64x64: generator only, batch %d clips x %d "
-                                   "frames, BatchNorm batch statistics, bf16" % (batch, video_len), "cuda_graph": False},
-            "achieved_tflops": frames * gflop_per_frame / ms, "frac_of_sustained_peak":
-            frames * gflop_per_frame / ms / peaks["bf16_sustained"]}
+            "value": frames / ms * 1e3, "unit": "frames/s (summed over ranks)", "n_gpus": world, "ms_per_batch": ms,
+            "config": {"workload": "BASELINE config 5%s: generator only, batch %d clips x %d frames of %dx%d per GPU, BatchNorm "
+                                   "batch statistics, bf16" % (" at the reference's native 64x64" if size == 64 else
+                                                                " as worded (128x128): EXTENSION architecture, parity unpinned",
+                                                                batch, video_len, size, size),
+                       "cuda_graph": graph is not None},
+            "achieved_tflops_per_gpu": batch * video_len * gf_per_frame / ms,
+            "frac_of_sustained_peak": batch * video_len * gf_per_frame / ms / peaks["bf16_sustained"]}
+
+
+def time_steps(torch, up, x_dev, t_dev, n, barrier):
+    """n replays of the captured step, bracketed by barrier + synchronize; device time in ms (this rank)."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(n):
+        up.step_host_inputs(x_dev, t_dev)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def max_over_ranks(torch, world, vals):
+    if world == 1:
+        return [float(v) for v in vals]
+    import torch.distributed as dist
+    tt = torch.tensor(list(vals), device="cuda", dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return [float(v) for v in tt]
+
+
+def train_leg(torch, K, parallel, args, model, rank, world, barrier, sampler=None):
+    """Builds the three networks + Updater for `model`, captures the step, does W warm-up replays and times K steps."""
+    up, it = build_updater(BATCH, parallel.shard_seed(1234, rank), use_graph=not args.no_graph, model=model)
+    x_dev = it.x[0].cuda()
+    t_dev = it.t[0].cuda()
+    # set-up (not warm-up): one eager step to count our kernel launches per step, then graph_warmup eager steps + capture
+    launches0 = K.launch_count()
+    up.step_host_inputs(x_dev, t_dev)
+    launches_per_step = K.launch_count() - launches0
+    while not args.no_graph and up._graph is None:
+        up.step_host_inputs(x_dev, t_dev)
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
+        up.step_host_inputs(x_dev, t_dev)
+    if sampler is not None:
+        sampler.start()
+        time.sleep(0.3)
+    ms = time_steps(torch, up, x_dev, t_dev, args.steps, barrier)
+    return up, it, x_dev, t_dev, ms, launches_per_step, warmup
 
 
 def run_ours(args):
@@ -327,7 +421,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     peaks = load_peaks()
     K.lib()
-    up, it = build_updater(BATCH, parallel.shard_seed(1234, rank), use_graph=not args.no_graph)
 
     def barrier():
         if world > 1:
@@ -335,26 +428,29 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-timed: inputs resident in HBM, K steps bracketed by barrier + synchronize, max over ranks
-    x_dev = it.x[0].cuda()
-    t_dev = it.t[0].cuda()
-    launches0 = K.launch_count()
-    up.step_host_inputs(x_dev, t_dev)      # first eager step: count our kernel launches per step
-    launches_per_step = K.launch_count() - launches0
-    for _ in range(max(args.warmup, 3) + 2):
-        up.step_host_inputs(x_dev, t_dev)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        up.step_host_inputs(x_dev, t_dev)
-    e1.record()
-    barrier()
-    ms_dev = e0.elapsed_time(e1)
+    sampler = ClockSampler(local) if rank == 0 else None
+    up, it, x_dev, t_dev, ms_dev, launches_per_step, warmup = train_leg(torch, K, parallel, args, args.model, rank, world,
+                                                                        barrier, sampler)
+    # ---- sustained: the same replay loop for >= 2 s (>= 5 windows of >= 100 steps), median window, its own clock record
+    sustained = None
+    if not args.no_sustained:
+        clocks_short = sampler.stop() if rank == 0 else None
+        sus_sampler = ClockSampler(local) if rank == 0 else None
+        if rank == 0:
+            sus_sampler.start()
+        win_steps, wins = max(100, args.steps), []
+        for _ in range(args.sustained_windows):
+            wins.append(max_over_ranks(torch, world, [time_steps(torch, up, x_dev, t_dev, win_steps, barrier)])[0])
+        sus_clocks = sus_sampler.stop() if rank == 0 else None
+        med = float(np.median(wins))
+        sustained = {"value": world * win_steps / (med / 1e3), "unit": "steps/s", "ms_per_step": med / win_steps,
+                     "windows": len(wins), "steps_per_window": win_steps, "window_ms": wins, "seconds": sum(wins) / 1e3,
+                     "stat": "median window, max over ranks per window", "clocks": sus_clocks}
+        if rank == 0:
+            sampler = ClockSampler(local)
+            sampler.start()
+    else:
+        clocks_short = None
     # ---- end to end through the public API: Updater.update() pulling uint8 clips from the pinned clip cache (iterator
     # -> sub-sequence draw -> pinned staging batch -> H2D -> step), losses read back each step
     cache = make_clip_cache(BATCH, parallel.shard_seed(1234, rank))
@@ -372,14 +468,44 @@ def run_ours(args):
     torch.cuda.synchronize()
     ms_e2e = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        tt = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e = float(tt[0]), float(tt[1])
+    if clocks_short is not None and clocks_short.get("samples"):
+        clocks = clocks_short if not clocks or not clocks.get("samples") else {
+            "sm_mhz": float(np.median([clocks_short["sm_mhz"], clocks["sm_mhz"]])),
+            "sm_max_mhz": max(clocks_short["sm_max_mhz"], clocks["sm_max_mhz"]),
+            "reasons": sorted(set(clocks_short["reasons"]) | set(clocks["reasons"])),
+            "samples": clocks_short["samples"] + clocks["samples"], "device_timed": clocks_short, "e2e": clocks}
+    ms_dev, ms_e2e = max_over_ranks(torch, world, [ms_dev, ms_e2e])
     assert K.tc_error_flag() == 0, "a tcgen05 kernel reported an mbarrier timeout"
     assert np.isfinite(loss_sink), "non-finite loss"
+    # ---- replicas: every rank must hold bit-identical parameters after the timed loops (BatchNorm running stats are local)
+    identical = parallel.replicas_identical([up.image_gen, up.image_dis, up.video_dis])
+    assert identical, "data-parallel replicas diverged"
+    exposed = getattr(up, "exposed_collective_ms", None)
 
-    layer_rows, stream_rows, dominant, cpu, gen = None, None, None, None, None
+    # ---- BASELINE config 4 (infogan) on the same N GPUs, same timing rules
+    other = None
+    if not args.no_other_model:
+        om = "infogan" if args.model == "normal" else "normal"
+        del up, cache
+        torch.cuda.empty_cache()
+        up2, _, _, _, ms2, lps2, _ = train_leg(torch, K, parallel, args, om, rank, world, barrier)
+        ms2 = max_over_ranks(torch, world, [ms2])[0]
+        ident2 = parallel.replicas_identical([up2.image_gen, up2.image_dis, up2.video_dis])
+        other = {"metric": "MoCoGAN train steps/s (bs35, 16x3x64x64)", "model": om, "value": world * args.steps / (ms2 / 1e3),
+                 "unit": "steps/s (summed over ranks)", "n_gpus": world, "ms_per_step": ms2 / args.steps, "steps": args.steps,
+                 "workload": "BASELINE config %s: MoCoGAN %s model, clips (35,3,16,64,64) per GPU" % ("4" if om == "infogan" else "2", om),
+                 "gpu_launches_per_step": int(lps2), "replicas_identical": bool(ident2)}
+        del up2
+        torch.cuda.empty_cache()
+    gen = gen128 = None
+    if not args.no_gen:
+        gen = gen_frames_per_s(torch, peaks, rank, world, barrier)
+        try:
+            gen128 = gen_frames_per_s(torch, peaks, rank, world, barrier, size=128, iters=4)
+        except ImportError:
+            gen128 = None
+
+    layer_rows, stream_rows, dominant, cpu = None, None, None, None
     if rank == 0:
         layer_rows = time_conv_layers(K, torch, peaks)
         stream_rows = time_stream_kernels(K, torch, peaks)
@@ -390,25 +516,31 @@ def run_ours(args):
         dominant = [r for r in layer_rows if (r["kernel"], r["layer"]) == dk][0]
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline_config1()
-        gen = gen_frames_per_s(torch, peaks) if world == 1 else None
     if rank != 0:
         return
     steps_per_s = world * args.steps / (ms_dev / 1e3)
     e2e_steps_per_s = world * args.steps / (ms_e2e / 1e3)
     conv_ms = sum(r["ms"] * r["calls_per_step"] for r in layer_rows)
+    traffic, traffic_file = load_traffic()
+    tkey = "%s:%s" % (dominant["kernel"], dominant["layer"])
+    cfg_no = "4" if args.model == "infogan" else "2"
     line = {
         "metric": "MoCoGAN train steps/s (bs35, 16x3x64x64)", "value": steps_per_s,
         "unit": "steps/s (batch-35 update_core steps, summed over ranks)", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3) + 3, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "warmup": warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "BASELINE config 2: MoCoGAN normal model (train.py MUG wiring), clips (35,3,16,64,64) "
-                               "per GPU, one update_core (G+Di+Dv) per step" + ("; data-parallel, NCCL all-reduce of the "
-                               "three flat gradient buffers" if world > 1 else ""),
+        "config": {"workload": "BASELINE config %s: MoCoGAN %s model (train.py MUG wiring), clips (35,3,16,64,64) "
+                               "per GPU, one update_core (G+Di+Dv) per step" % (cfg_no, args.model) +
+                               ("; data-parallel, NCCL all-reduce of the three flat gradient buffers" if world > 1 else ""),
                    "global_batch": BATCH * world, "parallelism": "dp%d" % world, "dp_overlap": parallel.describe() if world > 1 else None,
-                   "cuda_graph": up._graph is not None,
+                   "cuda_graph": not args.no_graph,
                    "l2": "no explicit flush: one step streams > 1 GB of activations/weights, >> 126 MB L2",
-                   "weights": "random init (GlorotNormal/LeCunNormal)", "noise": "device Philox"},
+                   "weights": "random init (GlorotNormal/LeCunNormal)", "noise": "device Philox",
+                   "setup": "1 eager step (launch count) + 2 eager + graph capture before the %d warm-up replays" % warmup},
         "clocks": clocks,
+        "sustained": sustained,
+        "replicas_identical": bool(identical),
+        "exposed_collective_ms": exposed,
         "e2e": {"value": e2e_steps_per_s, "unit": "steps/s",
                 "h2d_bytes_per_step": int(BATCH * 16 * 64 * 64 * 3 + BATCH * 4),
                 "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / args.steps,
@@ -417,39 +549,53 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": dominant["kernel"], "layer": dominant["layer"],
                      "achieved": dominant["tflops"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
                      "frac": dominant["frac_of_burst_peak"],
-                     "traffic": load_traffic().get("%s:%s" % (dominant["kernel"], dominant["layer"])),
+                     "traffic": None if traffic.get("stale") else traffic.get(tkey),
+                     "traffic_source": {"file": traffic_file, "csrc_sha_now": csrc_sha(), "csrc_sha_profiled": traffic.get("csrc_sha"),
+                                        "stale": bool(traffic.get("stale"))},
                      "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                      "algorithmic_flop_per_launch": dominant["gflop"] * 1e9, "peak_source": peaks["src"] + " (burst: kernel timed alone)",
                      "step": {"useful_gflop": USEFUL_GF_PER_STEP, "achieved_tflops": USEFUL_GF_PER_STEP * steps_per_s / world / 1e3,
                               "peak_sustained": peaks["bf16_sustained"],
                               "frac": USEFUL_GF_PER_STEP * steps_per_s / world / 1e3 / peaks["bf16_sustained"],
-                              "tc_conv_ms_per_step_isolated": conv_ms},
+                              "tc_conv_ms_per_step_isolated": conv_ms,
+                              "tc_conv_frac_of_burst_isolated": sum(r["gflop"] * r["calls_per_step"] for r in layer_rows) / conv_ms / peaks["bf16_burst"]},
                      "layers": layer_rows,
                      "hbm_kernels": {"peak_gb_per_s": peaks["hbm_gbs"], "peak_source": peaks["src"] + " (copy bandwidth)",
                                      "kernels": stream_rows}},
         "cpu_baseline": cpu,
+        "other_model": other,
         "gen": gen,
+        "gen128": gen128,
     }
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
-def oracle_step_time(config, batch, n_steps, as_executed=True, seed=0):
-    """Times the NumPy restatement of the reference's CPU step (im2col + BLAS, float32, three full backward passes)."""
+def oracle_stepper(config, batch, as_executed=True, seed=0):
+    """The NumPy restatement of the reference's CPU step (im2col + BLAS, float32, three full backward passes) as a
+    callable: step(i) runs the i-th update_core on the same models and returns its wall time in seconds."""
     from oracle import mocogan_ref as ref
     model, G, Di, Dv = ref.build_models(config, dtype=np.float32, seed=seed)
     up = ref.Updater(model, G, Di, Dv)
     C = G.out_channels
     x = np.random.default_rng(1234).uniform(-1, 1, size=(batch, C, 16, 64, 64)).astype(np.float32)
     t_real = np.random.default_rng(5).integers(0, 6, size=batch) if G.dim_zl else None
-    times = []
-    for i in range(n_steps + 1):
+
+    def step(i):
         t0 = time.perf_counter()
         # float64 randn then cast, as add_noise does (net.py:13); drawing is part of the reference's step
         r = ref.draw_step_randoms(np.random.default_rng(100 + i), np.random.default_rng(200 + i), G, Di, Dv, batch, x.shape,
                                   dtype=np.float32)
         up.update_core(x, t_real, r, as_executed=as_executed)
-        times.append(time.perf_counter() - t0)
+        return time.perf_counter() - t0
+
+    return step
+
+
+def oracle_step_time(config, batch, n_steps, as_executed=True, seed=0):
+    """One warm-up step, then n_steps timed ones (n_steps = 0: the warm-up step's own time)."""
+    step = oracle_stepper(config, batch, as_executed, seed)
+    times = [step(i) for i in range(n_steps + 1)]
     return times[1:] if n_steps > 0 else times
 
 
@@ -462,40 +608,58 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
-def cpu_baseline_config1():
-    """BASELINE config 1 (the reference's own CPU-runnable case): batch 8, (16,1,64,64), one as-executed step."""
-    times = oracle_step_time("mnist_normal", 8, 1, as_executed=True)
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms are meant to use all the host threads they can, so
+    the BLAS pools are set explicitly.  Returns the context manager that holds the limit (keep it alive)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        return None
+
+
+def cpu_baseline_config1(n_timed=3):
+    """BASELINE config 1 (the reference's own CPU-runnable case): batch 8, (16,1,64,64), as-executed steps; median of
+    `n_timed` timed steps after one warm-up step."""
+    hold = use_all_host_cores()
+    times = oracle_step_time("mnist_normal", 8, n_timed, as_executed=True)
     s = float(np.median(times))
+    del hold
     return {"value": 1.0 / s, "unit": "steps/s (batch-8 update_core steps, config 1)", "cores": cpu_threads(),
-            "kind": "port", "sample": "1 warm-up + 1 timed as-executed update_core of BASELINE config 1 (batch 8, "
-            "clips (16,1,64,64), float32 NumPy/BLAS restatement of the Chainer v3.1.0 CPU path; %.1f s)" % s,
-            "host_cpus": os.cpu_count()}
+            "kind": "port", "sample": "1 warm-up + %d timed as-executed update_core steps of BASELINE config 1 (batch 8, "
+            "clips (16,1,64,64), float32 NumPy/BLAS restatement of the Chainer v3.1.0 CPU path; median %.1f s, all %s)"
+            % (n_timed, s, ["%.1f" % t for t in times]), "host_cpus": os.cpu_count()}
 
 
 def run_reference(args):
     """Reference arm: the reference's CPU implementation of the path on the host cores (oracle port — genuine Chainer
-    3.1.0 cannot be imported here).  Each step is a bounded sample of the workload: `sample_batch`
-    clips of the 35, extrapolated linearly to batch 35."""
+    3.1.0 cannot be imported here), at BASELINE config 2's TRUE batch of 35 clips — no extrapolation.
+    One as-executed step is ~40 s on the box's cores, so the number of timed steps is bounded by a time budget
+    (>= 2 timed steps after one warm-up step) instead of taking --steps literally; `steps` reports what ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_batch = 2
-    t_probe = oracle_step_time("mug_normal", sample_batch, 0, as_executed=True)[0]   # doubles as warm-up
-    budget = 200.0
-    n = max(1, min(args.steps, int(budget / max(t_probe, 1e-3))))
-    times = oracle_step_time("mug_normal", sample_batch, n, as_executed=True)
+    hold = use_all_host_cores()
+    model = "mug_infogan" if args.model == "infogan" else "mug_normal"
+    step = oracle_stepper(model, BATCH, as_executed=True)
+    t_probe = step(0)                                                  # the warm-up step, timed to size the run
+    budget = float(os.environ.get("MCG_REF_BUDGET_S", "150"))
+    n = max(2, min(args.steps, int(budget / max(t_probe, 1e-3))))
+    times = [step(1 + i) for i in range(n)]
     s = float(np.median(times))
-    v = (sample_batch / float(BATCH)) / s
+    v = 1.0 / s
+    del hold
     line = {"impl": "reference", "metric": "MoCoGAN train steps/s (bs35, 16x3x64x64)", "value": v,
             "unit": "steps/s (batch-35 update_core steps, summed over ranks)", "n_gpus": args.gpus, "steps": n,
-            "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": 1, "ms_per_step": 1e3 * s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2: MoCoGAN normal model (train.py MUG wiring), clips (35,3,16,64,64), "
-                                   "one as-executed update_core per step, CPU"},
+            "config": {"workload": "BASELINE config %s: MoCoGAN %s model (train.py MUG wiring), clips (35,3,16,64,64), "
+                                   "one as-executed update_core per step, CPU" % ("4" if args.model == "infogan" else "2", args.model),
+                       "global_batch": BATCH, "note": "rank 0 only; a CPU step does not shard over GPUs"},
             "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cpu_threads(), "kind": "port",
-                             "sample": "%d timed steps at batch %d of 35 (%.2f s each), scaled by %d/35; float32 NumPy/BLAS "
-                                       "restatement of the Chainer v3.1.0 CPU path incl. its discarded backward work"
-                                       % (n, sample_batch, s, sample_batch), "host_cpus": os.cpu_count()},
+                             "sample": "1 warm-up + %d timed steps at the full batch of 35 (median %.1f s, all %s); float32 "
+                                       "NumPy/BLAS restatement of the Chainer v3.1.0 CPU path incl. its discarded backward work"
+                                       % (n, s, ["%.1f" % t for t in times]), "host_cpus": os.cpu_count()},
             "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -508,6 +672,12 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", choices=["normal", "infogan"], default="normal",
+                    help="normal = BASELINE config 2 (the headline); infogan = config 4.  The other one is timed as `other_model`.")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained leg")
+    ap.add_argument("--sustained-windows", type=int, default=5)
+    ap.add_argument("--no-other-model", action="store_true", help="skip the second model's (config 4) throughput leg")
+    ap.add_argument("--no-gen", action="store_true", help="skip the generator frames/s legs (config 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

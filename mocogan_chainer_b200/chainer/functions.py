@@ -282,7 +282,8 @@ class BNActNoise(FunctionNode):
                 self.mean, self.invstd = torch.empty(Cc, device=dev), torch.empty(Cc, device=dev)
                 K.bn_stats(yp, M, Cc, gamma.store, beta.store, bn.eps, bn.decay, self.mean, self.invstd, scale, shift,
                            bn.avg_mean, bn.avg_var)
-                bn.N += 1
+                # (the persistent N counts finetune-mode calls only in Chainer v3; the reference never finetunes, so
+                # its checkpoints hold N = 0 — and so do these)
             else:  # F.fixed_batch_normalization with the running statistics (util.py:92 is the only caller)
                 inv = torch.rsqrt(bn.avg_var + bn.eps)
                 scale = gamma.store * inv

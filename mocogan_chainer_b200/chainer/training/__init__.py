@@ -9,6 +9,12 @@ class StandardUpdater(object):
         self.converter = converter if converter is not _dataset.concat_examples else _to_device
         self.device = device
         self.iteration = 0
+        # Chainer's trainer registers every optimizer's target with the reporter under the optimizer's name, which is
+        # why updater.py:40,59 `chainer.report({'loss': ...}, dis)` yields 'image_dis/loss' etc. (train.py:146-148)
+        for name, opt in self._optimizers.items():
+            target = getattr(opt, "target", None)
+            if target is not None:
+                object.__setattr__(target, "report_name", name)
 
     @property
     def epoch(self):

@@ -1,10 +1,140 @@
-"""Datasets.  Only the OUTPUT CONTRACT of the reference's datasets.py matters to the hot path:
-float32 clips (C, T, H, W) in [-1, 0.992] and an int label or None (datasets.py:105-107,162-166).  The JPEG-decoding
-MUG / Moving-MNIST readers are out of scope; SyntheticClipDataset produces clips of that contract."""
+"""Datasets: the step before the hot path.  The OUTPUT CONTRACT of the reference's datasets.py
+is kept — float32 clips (C, T, H, W) = (v - 128) / 128 and an int label or None (datasets.py:105-107,162-166) — but
+the work is re-ordered for a 4 ms training step: MugDataset / MovingMnistDataset scan the same directory layout and
+decode every JPEG ONCE into uint8 frames (the reference decodes 16 JPEGs per example per epoch on the training thread,
+datasets.py:16-27,92); `get_example` then only slices and normalises, and `clip_cache()` hands the frames to
+Uint8ClipCache, which ships uint8 batches to the device.  SyntheticClipDataset produces clips of the same contract."""
+import glob
+import os
+import re
+from pathlib import Path
+
 import numpy as np
 import torch
 
 from .chainer.dataset import DatasetMixin
+
+frame_name_regex = re.compile(r'([0-9]+).jpg')
+
+
+def frame_number(name):
+    """datasets.py:12-14 — the sort key of a frame file.  (The reference compares the digit STRINGS; frames are written
+    zero-padded, datasets.py:138, so string and numeric order agree — kept as is.)"""
+    return re.search(frame_name_regex, str(name)).group(1)
+
+
+def read_video_u8(paths):
+    """datasets.py:16-27 `read_video`, kept in uint8: (T, H, W, C) (grey JPEGs: (T, H, W), as PIL yields them)."""
+    from PIL import Image
+    video = []
+    for path in paths:
+        with Image.open(path) as f:
+            video.append(np.asarray(f, dtype=np.uint8))
+    return np.asarray(video, dtype=np.uint8)
+
+
+def subsequence_idx(video_len, video_length, extract_speed):
+    """datasets.py:72-88 (MugDataset) / :141-147 (MovingMnistDataset, extract_speed = 0): the frames of one clip, with
+    the reference's np.random.randint draws."""
+    if video_len < video_length:
+        raise ValueError('invalid video length: {} < {}'.format(video_len, video_length))
+    if extract_speed and video_len > video_length * extract_speed:
+        needed = extract_speed * (video_length - 1)
+        gap = video_len - needed
+        start = 0 if gap == 0 else np.random.randint(0, gap, 1)[0]
+        return np.linspace(start, start + needed, video_length, endpoint=True, dtype=np.int32)
+    gap = video_len - video_length
+    start = 0 if gap == 0 else np.random.randint(0, gap, 1)[0]
+    return np.arange(start, start + video_length)
+
+
+class _DecodedVideoDataset(DatasetMixin):
+    """Shared by the two readers: self.videos = [(path, label | None)], frames decoded once on first use."""
+    extract_speed = 0
+
+    def __len__(self):
+        return len(self.videos)
+
+    def _frames(self, i):
+        if self._decoded[i] is None:
+            path = self.videos[i][0] if isinstance(self.videos[i], tuple) else self.videos[i]
+            paths = sorted(glob.glob(os.path.join(str(path), '*.jpg')), key=frame_number)
+            v = read_video_u8(paths)
+            if v.ndim != 4:
+                raise ValueError('invalid video shape: {}'.format(v.shape))
+            self._decoded[i] = v
+        return self._decoded[i]
+
+    def _label(self, i):
+        return self.videos[i][1] if isinstance(self.videos[i], tuple) else None
+
+    def get_example(self, i):
+        """return video shape: (ch, frame, height, width), float32 (v - 128) / 128; label int | None"""
+        frames = self._frames(i)
+        idx = subsequence_idx(len(frames), self.video_length, self.extract_speed)
+        video = (frames[idx].astype(np.float32) - 128.) / 128.
+        return video.transpose(3, 0, 1, 2), self._label(i)
+
+    def clip_cache(self, batch_size, shuffle=True, pin=True):
+        """The B200 input path: all videos as one pinned uint8 frame buffer + per-step uint8 batches (Uint8ClipCache)."""
+        vids = [self._frames(i) for i in range(len(self))]
+        labels = None if self._label(0) is None else [self._label(i) for i in range(len(self))]
+        return Uint8ClipCache(vids, labels, batch_size, self.video_length, self.extract_speed, shuffle, pin)
+
+
+class MugDataset(_DecodedVideoDataset):
+    """datasets.py:29-107: root/<category>/<video>/<frame>.jpg, six expression categories, videos shorter than
+    video_length discarded, long videos sub-sampled every extract_speed = 2 frames."""
+
+    def __init__(self, root_path, video_length=16):
+        self.root_path = Path(root_path)
+        self.video_length = video_length
+        self.extract_speed = 2
+        self.video_categories = list(self.root_path.glob("*"))
+        self.num_labels = len(self.video_categories)
+        category2num = {"anger": 0, "disgust": 1, "happiness": 2, "fear": 3, "sadness": 4, "surprise": 5}
+        self.videos = []
+        for category_path in self.video_categories:
+            if not category_path.is_dir():
+                continue
+            num_categ = category2num[category_path.name]
+            for video_path in sorted(category_path.glob("*")):
+                if not video_path.is_dir():
+                    continue
+                video_len = len(list(video_path.glob("*.jpg")))
+                if video_len >= video_length:
+                    self.videos.append((video_path, num_categ))
+                else:
+                    print(">> discarded {} (video length {} < {})\n".format(video_path.parent.name, video_len, video_length))
+        self._decoded = [None] * len(self.videos)
+
+
+class MovingMnistDataset(_DecodedVideoDataset):
+    """datasets.py:110-167: an .npy of (T, N, H, W) digits is written out once as 3-channel JPEG frames under
+    data/dataset/moving_mnist/preprocessed/<video>/<frame>.jpg, then read like any video; label None."""
+
+    def __init__(self, dataset_path, video_length=16, save_path="data/dataset/moving_mnist/preprocessed"):
+        self.video_length = video_length
+        save_path = Path(save_path)
+        if not save_path.exists():
+            self.preprocess(dataset_path, save_path)
+        self.videos = sorted(path for path in save_path.glob("*") if path.is_dir())
+        self._decoded = [None] * len(self.videos)
+
+    def preprocess(self, dataset_path, save_path):
+        from PIL import Image
+        print("\npreprocessing....")
+        videos = np.load(dataset_path)
+        videos = np.tile(videos[:, :, :, :, None], (1, 1, 1, 1, 3))
+        videos = videos.transpose(1, 0, 2, 3, 4)  # (N, T, H, W, C)
+        print("writing out {} videos:\n\t{} ---> {}".format(videos.shape[0], dataset_path, save_path))
+        save_path.mkdir(parents=True, exist_ok=True)
+        for i, video in enumerate(videos):
+            path = (save_path / "{:05d}".format(i))
+            path.mkdir(parents=True, exist_ok=True)
+            for j, img in enumerate(video):
+                Image.fromarray(img).save(path / "{:02d}.jpg".format(j))
+        print("")
 
 
 class SyntheticClipDataset(DatasetMixin):
@@ -49,6 +179,10 @@ class Uint8ClipCache(object):
             self._stage = [t.pin_memory() for t in self._stage]
             self._lab = [t.pin_memory() for t in self._lab]
         self._k = 0
+        # per staging buffer: the CUDA event recorded after the host->device copy that last read it (note_copy); next()
+        # waits for it on the HOST before refilling the buffer, so a copy still queued on the device cannot see the
+        # next batch's bytes however far the host runs ahead
+        self._copied = [None] * len(self._stage)
         n = len(lens)
         self._order = np.random.permutation(n) if shuffle else np.arange(n)
         self.current_position, self.epoch, self.is_new_epoch = 0, 0, False
@@ -86,13 +220,20 @@ class Uint8ClipCache(object):
             self.current_position = i_end
         rows = np.concatenate([self._clip_rows(int(v)) for v in ids])
         k = self._k = (self._k + 1) % len(self._stage)      # three staging buffers: one being filled, two in flight
+        if self._copied[k] is not None:
+            self._copied[k].synchronize()                   # the H2D copy that read this buffer has executed
+            self._copied[k] = None
         stage = self._stage[k]
         torch.index_select(self.frames, 0, torch.from_numpy(rows.astype(np.int64)), out=stage.view((-1,) + tuple(stage.shape[2:])))
         t = None
         if self.labels is not None:
             t = self._lab[k]
             t.copy_(torch.from_numpy(self.labels[np.asarray(ids, dtype=np.int64)]))
-        return StackedBatch(stage.permute(0, 4, 1, 2, 3), t)   # logical (N, C, T, H, W) view of channels-last uint8
+        return StackedBatch(stage.permute(0, 4, 1, 2, 3), t, owner=self, slot=k)   # logical (N,C,T,H,W) view, uint8
+
+    def note_copy(self, slot, event):
+        """Called by whoever copies a batch to the device: `event` completes when the copy has read staging buffer `slot`."""
+        self._copied[slot] = event
 
     __next__ = next
 
@@ -113,9 +254,14 @@ class Uint8ClipCache(object):
 class StackedBatch(list):
     """A batch that is already stacked: (x, t) tensors; `chainer.dataset.concat_examples` passes it through."""
 
-    def __init__(self, x, t):
+    def __init__(self, x, t, owner=None, slot=None):
         super(StackedBatch, self).__init__()
-        self.x, self.t = x, t
+        self.x, self.t, self.owner, self.slot = x, t, owner, slot
+
+    def copied(self, event):
+        """Report the CUDA event that follows this batch's host->device copy back to the cache that owns its memory."""
+        if self.owner is not None:
+            self.owner.note_copy(self.slot, event)
 
     def __len__(self):
         return self.x.shape[0]

@@ -33,6 +33,9 @@ class Updater(chainer.training.StandardUpdater):
         # additive: in graph mode, copy batch i+1 host->device on a copy stream while step i runs
         self.prefetch = kwargs.pop('prefetch', True)
         self._stage, self._stage_next, self._copy_stream, self._flags = None, None, None, None
+        # additive: parity tests set this to read the forward's Variables (x_fake, y_*) after a step
+        self.keep_forward = kwargs.pop('keep_forward', False)
+        self.last_forward = None
 
         super(Updater, self).__init__(*args, **kwargs)
         self.losses = {}
@@ -62,6 +65,19 @@ class Updater(chainer.training.StandardUpdater):
             chainer.report({'loss': loss.data}, link)
             if self.tf_writer is not None:
                 self.tf_writer.add_scalar('loss:{}'.format(link.name), float(loss.data), self.epoch)
+
+    def _report_replayed(self):
+        """Graph mode: the loss nodes are not re-executed on replay, so the new-epoch report of updater.py:39-42,58-61
+        reads the captured step's static loss tensors instead."""
+        if not self.is_new_epoch:
+            return
+        for link in (self.image_dis, self.video_dis, self.image_gen):
+            loss = self.losses.get(link.name)
+            if loss is None:
+                continue
+            chainer.report({'loss': loss}, link)
+            if self.tf_writer is not None:
+                self.tf_writer.add_scalar('loss:{}'.format(link.name), float(loss), self.epoch)
 
     def concat_label_video(self, video, label, xp=None):
         """updater.py:65-76 (cgan): append dim_zl planes of -1 with +1 at the label plane.  A FunctionNode, so the fake
@@ -126,6 +142,10 @@ class Updater(chainer.training.StandardUpdater):
             with torch.cuda.stream(st_dvf):
                 y_fake_v = video_dis(x_fake)              # updater.py:108
 
+            if self.keep_forward:
+                self.last_forward = dict(x_fake=x_gen, y_real_i=y_real_i, y_real_v=y_real_v, y_fake_i=y_fake_i,
+                                         y_fake_v=y_fake_v)
+
             ## update  (updater.py:111-113)
             # passes A, B: gradients flowing from the discriminator losses into the generator are discarded by the
             # reference (image_gen.cleargrads() in pass C) -> not computed.  pass C: discriminator wgrads are discarded.
@@ -155,7 +175,17 @@ class Updater(chainer.training.StandardUpdater):
         x_real, t_real = concat_examples(batch)
         if t_real is not None and not torch.is_tensor(t_real):
             t_real = np.asarray(t_real).astype(np.int32)
+        # a batch that lives in re-used pinned staging memory (datasets.Uint8ClipCache) wants to know when its
+        # host->device copy has executed, so that the buffer is not refilled under a copy still queued on the device
+        self._copied_cb = getattr(batch, "copied", None)
         return x_real, t_real, (it.is_new_epoch, it.epoch)
+
+    def _report_copied(self, stream=None):
+        cb, self._copied_cb = getattr(self, "_copied_cb", None), None
+        if cb is not None:
+            ev = torch.cuda.Event()
+            ev.record(stream if stream is not None else torch.cuda.current_stream())
+            cb(ev)
 
     @property
     def is_new_epoch(self):
@@ -174,6 +204,7 @@ class Updater(chainer.training.StandardUpdater):
             return self.step_host_inputs(x_real, t_real)
         x_real = self.converter(x_real, self.device)
         t_real = None if t_real is None else self.converter(t_real, self.device)
+        self._report_copied()
         self.step_on_device(x_real, t_real)
 
     def _issue_h2d(self, k, host):
@@ -197,6 +228,7 @@ class Updater(chainer.training.StandardUpdater):
             if t is not None:
                 slot["t"].copy_(t, non_blocking=True)
             slot["ready"].record(cs)
+        self._report_copied(cs)
         slot["flags"] = flags
 
     def _update_core_prefetched(self):
@@ -225,6 +257,7 @@ class Updater(chainer.training.StandardUpdater):
         if not self.use_graph:
             x_real = self.converter(x_real, self.device)
             t_real = None if t_real is None else self.converter(t_real, self.device)
+            self._report_copied()
             return self.step_on_device(x_real, t_real)
         as_t = lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
         x_real = as_t(x_real)
@@ -237,8 +270,10 @@ class Updater(chainer.training.StandardUpdater):
         sx.copy_(x_real, non_blocking=True)
         if st is not None:
             st.copy_(t_real, non_blocking=True)
+        self._report_copied()
         if self._graph is not None:
             self._graph.replay()
+            self._report_replayed()
             return
         if self._eager_steps < self.graph_warmup:
             self._eager_steps += 1
@@ -249,6 +284,7 @@ class Updater(chainer.training.StandardUpdater):
             self.step_on_device(sx, st)
         self._graph = g
         g.replay()
+        self._report_replayed()
 
 
 def _lab(t):

@@ -177,3 +177,28 @@ def describe():
 def shard_seed(base_seed, rank):
     """rank r uses seed base+r for its clips, latents and noise."""
     return int(base_seed) + int(rank)
+
+
+def replica_checksums(links):
+    """Two position-sensitive integer checksums of each model's fp32 parameter arena (bit patterns, not values): equal
+    on every rank iff the replicas are bit-identical.  torch ops on the arena — bookkeeping, not the step."""
+    sums = []
+    for link in links:
+        bits = link.arena().data.view(torch.int32).to(torch.int64)
+        idx = torch.arange(bits.numel(), device=bits.device, dtype=torch.int64) % 65521 + 1
+        sums += [bits.sum(), (bits * idx).sum()]
+    return torch.stack(sums)
+
+
+def replicas_identical(links, group=None):
+    """True iff every rank holds bit-identical parameters for all `links` (BatchNorm running statistics are local by
+    design, SURVEY.md §8e, and not part of the check).  Collective: call on every rank."""
+    mine = replica_checksums(links)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return True
+    w = dist.get_world_size(group)
+    if dist.get_backend(group) == "gloo":
+        mine = mine.cpu()
+    gathered = [torch.empty_like(mine) for _ in range(w)]
+    dist.all_gather(gathered, mine, group=group)
+    return all(bool(torch.equal(gathered[0], g)) for g in gathered[1:])

@@ -1,9 +1,11 @@
 """train.py of raahii/mocogan-chainer on the B200-native step (train.py:24-195).
 
 Every reference flag is kept with its default (train.py:26-44), including --n_filters_idis/--n_filters_vdis which the
-reference parses but never uses (App. B#4).  Additive flags: --synthetic, --dtype, --seed, --graph, --max_iter.
-The Chainer Trainer/extension plumbing is replaced by a plain loop with the same epoch-triggered actions
-(loss report, model snapshots with the reference's file names)."""
+reference parses but never uses (App. B#4).  Additive flags: --synthetic, --dtype, --seed, --graph, --max_iter, --no_clip_cache.
+The Chainer Trainer/extension plumbing is replaced by a plain loop with the same epoch-triggered actions: LogReport's
+`log` file and the PrintReport line (train.py:146-151), model / trainer snapshots with the reference's file names
+(train.py:135-144), and log_tensorboard's sample grids (train.py:154-160, util.py:89-115)."""
+import json
 import argparse
 import os
 import sys
@@ -20,7 +22,8 @@ if __package__ in (None, ""):
 from . import chainer  # noqa: E402
 from . import parallel  # noqa: E402
 from . import random as mrandom  # noqa: E402
-from .datasets import SyntheticClipDataset  # noqa: E402
+from . import util  # noqa: E402
+from .datasets import MovingMnistDataset, MugDataset, SyntheticClipDataset  # noqa: E402
 from .model.net import ImageDiscriminator, ImageGenerator, VideoDiscriminator  # noqa: E402
 from .model.updater import Updater  # noqa: E402
 
@@ -53,6 +56,8 @@ def build_parser():
     parser.add_argument('--seed', type=int, default=0)
     parser.add_argument('--graph', action='store_true', help='replay the step as a CUDA graph')
     parser.add_argument('--max_iter', type=int, default=0, help='stop after this many iterations (0: --max_epoch rules)')
+    parser.add_argument('--no_clip_cache', action='store_true',
+                        help='feed float32 examples through SerialIterator as the reference does, instead of the uint8 clip cache')
     return parser
 
 
@@ -96,27 +101,48 @@ def main(argv=None):
     rank, world = parallel.init_from_env()
     chainer.config.compute_dtype = args.dtype
     np.random.seed(args.seed)
-    if not args.synthetic:
-        raise SystemExit("the MUG / Moving-MNIST JPEG readers are out of scope of this build (SURVEY.md §2a #5); "
-                         "pass --synthetic N to train on synthetic clips of the same contract")
-    train_dataset = SyntheticClipDataset(args.synthetic, channel, video_length, size, num_labels,
-                                         seed=parallel.shard_seed(1234, rank))
-    train_iter = chainer.iterators.SerialIterator(train_dataset, args.batchsize)
+    # device: the reference's default --gpu -1 means "CPU"; this build has no CPU path (the kernels are the product), so a
+    # negative id is an error rather than a silent move to device 0.  Under torchrun every rank owns the GPU LOCAL_RANK
+    # names, whatever --gpu says.
+    if world > 1:
+        device = int(os.environ.get("LOCAL_RANK", rank))
+    elif args.gpu < 0:
+        raise ValueError("--gpu {}: this build runs on a CUDA device only (no CPU fallback); pass --gpu 0".format(args.gpu))
+    else:
+        device = args.gpu
+    chainer.cuda.get_device_from_id(device).use()
+    if args.synthetic:
+        train_dataset = SyntheticClipDataset(args.synthetic, channel, video_length, size, num_labels,
+                                             seed=parallel.shard_seed(1234, rank))
+    elif args.dataset_type == "mug":       # train.py:60-62
+        train_dataset = MugDataset(args.dataset, video_length)
+    elif args.dataset_type == "mnist":     # train.py:63-65
+        train_dataset = MovingMnistDataset(args.dataset, video_length)
+    else:
+        raise NotImplementedError
+    if hasattr(train_dataset, "clip_cache") and not args.no_clip_cache:
+        # videos decoded once, uint8 batches assembled in pinned memory and normalised on the device
+        train_iter = train_dataset.clip_cache(args.batchsize)
+    else:
+        train_iter = chainer.iterators.SerialIterator(train_dataset, args.batchsize)
     image_gen, image_dis, video_dis = build_models(args.model, args.dim_zc, args.dim_zm, num_labels, channel,
                                                    args.n_filters_gen, video_length, use_noise, noise_sigma)
-    if args.gpu >= 0:
-        chainer.cuda.get_device_from_id(args.gpu).use()
     opts = {'image_gen': make_optimizer(image_gen, 2e-4, 5e-5, 0.999),
             'image_dis': make_optimizer(image_dis, 2e-4, 5e-5, 0.999),
             'video_dis': make_optimizer(video_dis, 2e-4, 5e-5, 0.999)}
     parallel.attach(list(opts.values()))
     mrandom.set_source(mrandom.DeviceRandom(seed=parallel.shard_seed(args.seed, rank), video_length=video_length))
-    updater = Updater(model=args.model, models=(image_gen, image_dis, video_dis), video_length=video_length,
-                      img_size=size, channel=channel, dim_zl=num_labels, iterator=train_iter, tensorboard_writer=None,
-                      optimizer=opts, device=max(args.gpu, 0), use_graph=args.graph)
     save_path = Path('result') / args.save_name
+    writer = None
     if rank == 0:
         save_path.mkdir(parents=True, exist_ok=True)
+        if args.log_tensorboard_interval > 0:
+            writer = util.make_writer(Path('runs') / args.save_name)          # train.py:103
+    updater = Updater(model=args.model, models=(image_gen, image_dis, video_dis), video_length=video_length,
+                      img_size=size, channel=channel, dim_zl=num_labels, iterator=train_iter, tensorboard_writer=writer,
+                      optimizer=opts, device=device, use_graph=args.graph)
+    log_samples = util.log_tensorboard(image_gen, args.num_gen_samples, video_length, writer) if writer is not None else None
+    log_entries = []
     trainer_state = chainer.training.TrainerState(updater)
     if args.resume:
         # train.py:162-163 `serializers.load_npz(args.resume, trainer)`: a full-trainer snapshot_epoch_N.npz restores the
@@ -143,6 +169,14 @@ def main(argv=None):
                                              ls.get('ImageDiscriminator', float('nan')),
                                              ls.get('VideoDiscriminator', float('nan')),
                                              updater.iteration / (time.time() - t0)))
+                # extensions.LogReport (train.py:146-147): result/<save_name>/log, one JSON entry per trigger
+                log_entries.append({"epoch": ep, "iteration": updater.iteration, "elapsed_time": time.time() - t0,
+                                    "image_gen/loss": ls.get('ImageGenerator'), "image_dis/loss": ls.get('ImageDiscriminator'),
+                                    "video_dis/loss": ls.get('VideoDiscriminator')})
+                with open(save_path / 'log', 'w') as f:
+                    json.dump(log_entries, f, indent=4)
+            if log_samples is not None and ep % args.log_tensorboard_interval == 0:
+                log_samples(updater)                                              # train.py:154-160
             if ep % args.snapshot_interval == 0:
                 chainer.serializers.save_npz(save_path / 'snapshot_epoch_{}.npz'.format(ep), trainer_state)   # train.py:137
                 chainer.serializers.save_npz(save_path / 'image_gen_epoch_{}.npz'.format(ep), image_gen)
@@ -152,6 +186,8 @@ def main(argv=None):
         chainer.serializers.save_npz(save_path / 'image_gen_epoch_fianl.npz', image_gen)   # sic, train.py:190-192
         chainer.serializers.save_npz(save_path / 'image_dis_epoch_fianl.npz', image_dis)
         chainer.serializers.save_npz(save_path / 'video_dis_epoch_fianl.npz', video_dis)
+        if writer is not None:
+            writer.close()
     return updater
 
 

@@ -63,7 +63,9 @@ class ImageGenerator:
         lat["zc"] = rng.normal(0, 0.33, size=(batchsize, dim_zc)).astype(dtype)
         return lat
 
-    def forward(self, batchsize, lat, update_running=True):
+    def forward(self, batchsize, lat, update_running=True, train=True):
+        """train=False: chainer.config.train == False, i.e. L.BatchNormalization runs F.fixed_batch_normalization with
+        the running statistics (the util.py:92 `log_tensorboard` path); no statistics are updated."""
         p, T, N, dt = self.params, self.video_len, batchsize, self.dtype
         cache = {"N": N}
         # make_zm  net.py:61-81
@@ -86,7 +88,12 @@ class ImageGenerator:
         for i in range(1, 6):
             W, b = p["dc%d/W" % i], p["dc%d/b" % i]
             y = ops.deconv_nd_fwd(x, W, b, self.strides[i - 1], self.pads[i - 1])
-            if i < 5:
+            if i < 5 and not train:
+                bn = ops.batchnorm_fixed(y, p["bn%d/gamma" % i], p["bn%d/beta" % i], self.persistent["bn%d/avg_mean" % i],
+                                         self.persistent["bn%d/avg_var" % i])
+                out = np.maximum(bn, 0)
+                acts.append((x, y, None, out, bn))
+            elif i < 5:
                 am = self.persistent["bn%d/avg_mean" % i] if update_running else None
                 av = self.persistent["bn%d/avg_var" % i] if update_running else None
                 bn, stats = ops.batchnorm_fwd(y, p["bn%d/gamma" % i], p["bn%d/beta" % i], am, av)

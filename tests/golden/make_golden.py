@@ -17,6 +17,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle import mocogan_ref as ref  # noqa: E402
 
+GRAD_SAMPLE = 4096   # gradients are stored whole up to this many elements, beyond that as every k-th element
+
+
+def grad_sample(g):
+    """The elements of a gradient tensor the fixtures keep: all of it, or a fixed stride through the flattened array."""
+    flat = np.asarray(g).reshape(-1)
+    return flat[::max(1, -(-flat.size // GRAD_SAMPLE))]
+
+
 CASES = {"mnist_normal": dict(config="mnist_normal", nf=8, N=2), "mug_infogan": dict(config="mug_infogan", nf=8, N=3),
          "mug_cgan": dict(config="mug_cgan", nf=8, N=2)}
 
@@ -50,6 +59,9 @@ def run_case(config, nf, N):
     for name, key in (("g", "grads_g"), ("di", "grads_di"), ("dv", "grads_dv")):
         for k, v in trace[key].items():
             out["gradnorm_%s_%s" % (name, k.replace("/", "_"))] = np.float64(np.linalg.norm(v))
+            out["grad_%s_%s" % (name, k.replace("/", "_"))] = grad_sample(v).astype(np.float32)
+    for key in ("y_real_i", "y_real_v", "y_fake_i", "y_fake_v"):
+        out[key] = trace[key].astype(np.float32)
     for name, net in (("g", G), ("di", Di), ("dv", Dv)):
         out["post_%s_dc5_W" % name] = net.params["dc5/W"].astype(np.float32)
         for k, v in net.persistent.items():

@@ -1,9 +1,11 @@
 """Host-side logic that needs no GPU: the autograd sweep, dead-branch pruning, link/parameter naming (the npz key
 schema of SURVEY.md App. D), iterators, flags."""
 import numpy as np
+import pytest
 import torch
 
 from mocogan_chainer_b200 import chainer
+from oracle import mocogan_ref as ref
 from mocogan_chainer_b200.chainer import FunctionNode, Variable
 
 
@@ -224,3 +226,105 @@ def test_concat_label_video_node_matches_oracle_and_slices_the_video_gradient():
     yr = F.concat_label_video(Variable(u8, requires_grad=False), lab, L)
     assert not yr.requires_grad
     assert np.array_equal(yr.data.numpy(), ref.concat_label_video((u8.numpy().astype(np.float32) - 128.) / 128., lab.numpy(), L))
+
+
+def _write_video(path, frames):
+    from PIL import Image
+    path.mkdir(parents=True, exist_ok=True)
+    for j, img in enumerate(frames):
+        Image.fromarray(img).save(path / "{:02d}.jpg".format(j), quality=95)
+
+
+def test_mug_dataset_follows_datasets_py(tmp_path):
+    """datasets.py:29-107 — directory scan, category labels, short videos discarded, sub-sequence rule with the same
+    np.random draws, (v - 128) / 128, (C, T, H, W); and the uint8 clip cache built from it hands out the same clips."""
+    from mocogan_chainer_b200.datasets import MugDataset, read_video_u8
+    rng = np.random.default_rng(0)
+    lens = {("happiness", "a"): 40, ("happiness", "b"): 20, ("fear", "c"): 33, ("fear", "short"): 10}
+    for (cat, vid), n in lens.items():
+        _write_video(tmp_path / cat / vid, rng.integers(0, 256, size=(n, 64, 64, 3), dtype=np.uint8))
+    ds = MugDataset(tmp_path, video_length=16)
+    assert len(ds) == 3 and ds.num_labels == 2 and ds.extract_speed == 2
+    labels = {p.name: lab for p, lab in ds.videos}
+    assert labels == {"a": 2, "b": 2, "c": 3}
+    for i, (path, lab) in enumerate(ds.videos):
+        stored = read_video_u8(sorted(str(p) for p in path.glob("*.jpg")))
+        np.random.seed(7 + i)
+        video, categ = ds.get_example(i)
+        assert video.shape == (3, 16, 64, 64) and video.dtype == np.float32 and categ == lab
+        draws = []
+        np.random.seed(7 + i)
+        idx = ref.subsequence_indices(len(stored), 16, 2, lambda gap: draws.append(gap) or np.random.randint(0, gap, 1)[0])
+        assert np.array_equal(video, ref.normalize_clip(stored[idx]))
+        if len(stored) == 40:          # > 16 * 2 frames: every 2nd frame (np.linspace over 31 frames)
+            assert idx[-1] - idx[0] == 30
+    cache = ds.clip_cache(2, shuffle=False, pin=False)
+    np.random.seed(3)
+    b = cache.next()
+    np.random.seed(3)
+    want = [ds.get_example(i) for i in (0, 1)]
+    got = (b.x.numpy().astype(np.float32) - 128.) / 128.
+    assert b.x.dtype == torch.uint8 and tuple(b.x.shape) == (2, 3, 16, 64, 64)
+    assert np.array_equal(got, np.stack([w[0] for w in want])) and b.t.tolist() == [w[1] for w in want]
+
+
+def test_moving_mnist_dataset_follows_datasets_py(tmp_path):
+    """datasets.py:110-167 — (T, N, H, W) .npy written out once as 3-channel JPEG frames, contiguous 16-frame windows,
+    label None."""
+    from mocogan_chainer_b200.datasets import MovingMnistDataset
+    arr = np.random.default_rng(1).integers(0, 256, size=(20, 3, 64, 64), dtype=np.uint8)
+    np.save(tmp_path / "mnist.npy", arr)
+    ds = MovingMnistDataset(tmp_path / "mnist.npy", 16, save_path=tmp_path / "pre")
+    assert len(ds) == 3 and len(list((tmp_path / "pre" / "00000").glob("*.jpg"))) == 20
+    np.random.seed(0)
+    video, label = ds.get_example(1)
+    assert video.shape == (3, 16, 64, 64) and video.dtype == np.float32 and label is None
+    assert -1.0 <= video.min() and video.max() <= 127. / 128.
+    assert np.array_equal(video[0], video[1])       # grey digits tiled to three channels
+    ds2 = MovingMnistDataset(tmp_path / "mnist.npy", 16, save_path=tmp_path / "pre")   # second run: no re-preprocessing
+    assert len(ds2) == 3
+
+
+def test_clip_cache_waits_for_the_copy_that_read_a_staging_buffer():
+    """A staging buffer is refilled only after the event reported for the copy that last read it has completed."""
+    from mocogan_chainer_b200.datasets import Uint8ClipCache
+    vids = [np.full((20, 4, 4, 3), i, dtype=np.uint8) for i in range(4)]
+    cache = Uint8ClipCache(vids, [0, 1, 2, 3], 2, video_length=16, extract_speed=2, shuffle=False, pin=False)
+
+    class Ev(object):
+        def __init__(self):
+            self.waited = False
+
+        def synchronize(self):
+            self.waited = True
+
+    evs = []
+    for _ in range(3):
+        b = cache.next()
+        ev = Ev()
+        b.copied(ev)
+        evs.append((b.slot, ev))
+    assert not any(e.waited for _, e in evs)          # three buffers: nothing re-used yet
+    b = cache.next()                                  # fourth batch re-uses the first buffer
+    assert b.slot == evs[0][0] and evs[0][1].waited and not evs[1][1].waited
+
+
+def test_report_keys_and_train_device_rules(monkeypatch):
+    """chainer.report keys follow the optimizer names ('image_dis/loss', train.py:146-151); --gpu -1 is rejected."""
+    from mocogan_chainer_b200 import chainer, train
+    from mocogan_chainer_b200.chainer.training import StandardUpdater
+
+    class L_(chainer.Link):
+        pass
+
+    class O_(object):
+        def __init__(self, t):
+            self.target = t
+
+    link = L_()
+    link.name = "ImageDiscriminator"
+    StandardUpdater(iterator=None, optimizer={"image_dis": O_(link)})
+    chainer.report({"loss": 1.5}, link)
+    assert chainer.get_report()["image_dis/loss"] == 1.5
+    with pytest.raises(ValueError):
+        train.main(["--synthetic", "4", "--batchsize", "2"])       # default --gpu -1

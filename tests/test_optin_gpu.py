@@ -1,7 +1,7 @@
 """The opt-in scheduling paths stay parity-green: programmatic dependent launch (MCG_PDL=1) and dynamic work distribution
 of the persistent fprop/dgrad kernels (MCG_TC_DYN=1).  Both are read once per process, so each case runs in a child
-pytest process with the flag set: the BASELINE config-2 layer sizes of the tcgen05 kernels against the independent
-fp32 kernel (only those are large enough for the dynamic distribution to switch on) and one whole update_core step
+pytest process with the flag set: the BASELINE config-2 layer sizes of the tcgen05 kernels against the float64
+host convolution (only those are large enough for the dynamic distribution to switch on) and one whole update_core step
 against the oracle."""
 import os
 import subprocess
@@ -16,7 +16,7 @@ SELECT = {
     # every kernel of a step launched with the programmatic-serialization attribute, eager and multi-stream
     "MCG_PDL": STEP + ["tests/test_step_gpu.py::test_step_fp32_strict_infogan"],
     # the dynamic distribution only switches on when a CTA has >= 4 tile steps: the full-size layers
-    "MCG_TC_DYN": ["tests/test_kernels_gpu.py::test_conv_tc_full_size_vs_simt"] + STEP,
+    "MCG_TC_DYN": ["tests/test_kernels_gpu.py::test_conv_tc_full_size_vs_float64"] + STEP,
 }
 
 

@@ -1,12 +1,18 @@
 """Whole-step parity: Updater.step_on_device (the CUDA path behind the reference's update_core) against the
 NumPy oracle's update_core on identical weights and identical injected random tensors.
 
-Checked per step: the generator's clip, all four discriminator outputs, the three losses, every parameter
-gradient of passes A, B, C (including the stale-activation / fresh-weight semantics of pass C), the BatchNorm
-running statistics, and the post-step weights (Adam + WeightDecay).
-Tolerances: fp32 mode 1e-5 (losses) / 1e-4 (gradients, which chain ~10 fp32 kernels); bf16 mode 2e-2 on the losses,
-gradient direction (cosine > 0.95) for whole-network gradients (the 2e-2 per-layer bound lives in test_kernels_gpu.py).
+Checked per step: the generator's clip, all four discriminator outputs, every layer's input and convolution output
+and the BatchNorm batch statistics of the five network calls (`check_forward`, against trace["cache_*"]), the three
+losses, every parameter gradient of passes A, B, C (including the stale-activation / fresh-weight semantics of pass
+C), the BatchNorm running statistics, and the post-step weights (Adam + WeightDecay).
+Tolerances (max|a-b| / max|b| per tensor): fp32 mode 1e-5 on losses, outputs and activations, 1e-4 on gradients (which
+chain ~10 fp32 kernels); bf16 mode 2e-2 on losses, outputs and activations.  bf16 whole-network gradients: bf16
+storage flips (Leaky)ReLU masks and the discriminator losses back-propagate from ONE sample (updater.py:25-26), so the
+element-wise bound is per parameter group (BF16_GRAD_BOUNDS: what was measured on B200 plus margin) and every tensor
+must also agree in direction; the <= 2e-2 per-layer bound on identical inputs lives in test_kernels_gpu.py.
 """
+import json
+import os
 import numpy as np
 import pytest
 import torch
@@ -20,6 +26,109 @@ pytestmark = pytest.mark.gpu
 def relerr(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def chain_nodes(var, stop_at=None):
+    """FunctionNodes on the first-input chain that produced `var`, first executed first (optionally from the last node
+    of type `stop_at` on)."""
+    nodes, v = [], var
+    while v is not None and v.creator_node is not None:
+        n = v.creator_node
+        nodes.append(n)
+        if stop_at is not None and isinstance(n, stop_at):
+            break
+        v = n.inputs[0]
+    return nodes[::-1]
+
+
+def logical(t5):
+    """channels-last (N,T,H,W,C) device storage -> float64 NumPy (N,C,T,H,W)."""
+    return t5.float().permute(0, 4, 1, 2, 3).cpu().numpy().astype(np.float64)
+
+
+# Two kinds of tensor get a stated slack over the per-layer tolerance (measured on B200, profiles/r02_parity_report.json):
+#  * the four logits: an 8,192- to 32,768-term dot product of O(1) terms that cancels to O(0.1), at the END of five
+#    chained layers — fp32 mode reaches 1.4e-5 of max|y| (mnist shapes) where every layer tensor stays below 7e-6;
+#  * x_fake: the output of five chained bf16 layers compared on tanh's absolute scale (max = 1): 1.8e-2 .. 2.3e-2, while
+#    every single layer's input and output stays below 1.2e-2.
+FORWARD_SLACK = {"y_real_i": 3.0, "y_real_v": 3.0, "y_fake_i": 3.0, "y_fake_v": 3.0, "x_fake": 1.5}
+
+
+def check_forward(up, trace, oG, tol, report=None):
+    """x_fake, the four discriminator outputs and every layer of the five network calls against the oracle's trace:
+    the input each convolution read (previous activation + add_noise), its output (pre-BatchNorm, bias included) and
+    the batch statistics BatchNorm normalised with."""
+    from mocogan_chainer_b200.chainer import functions as F
+    fw = up.last_forward
+    errs = {}
+
+    def cmp(tag, got, want):
+        want = np.asarray(want, np.float64)
+        got = np.asarray(got, np.float64).reshape(want.shape)
+        errs[tag] = relerr(got, want)
+
+    C = oG.out_channels
+    xf = fw["x_fake"].data.float().permute(2, 0, 1, 3, 4)[:, :, :C].cpu().numpy()     # (N,C[+zl],T,H,W) -> (T,N,C,H,W)
+    cmp("x_fake", xf, trace["x_fake"])
+    for key in ("y_real_i", "y_real_v", "y_fake_i", "y_fake_v"):
+        cmp(key, fw[key].data.float().cpu().numpy(), trace[key])
+    for key, cache in (("y_real_i", "cache_ri"), ("y_real_v", "cache_rv"), ("y_fake_i", "cache_fi"), ("y_fake_v", "cache_fv")):
+        nodes = chain_nodes(fw[key], stop_at=F.PackVideo)
+        convs = [n for n in nodes if isinstance(n, F.ConvolutionND)]
+        bns = [n for n in nodes if isinstance(n, F.BNActNoise)]
+        assert len(convs) == 5 and len(bns) == 4, (key, [type(n).__name__ for n in nodes])
+        acts = trace[cache]["acts"]
+        for i, cv in enumerate(convs):
+            h = acts[i][0]
+            got = logical(cv.xp)
+            cmp("%s.dc%d.in" % (key, i + 1), got[:, :, 0] if h.ndim == 4 else got, h)
+        for i, bn in enumerate(bns):
+            y, stats = acts[i][1], acts[i][2]
+            got = logical(bn.yp)
+            cmp("%s.dc%d.out" % (key, i + 1), got[:, :, 0] if y.ndim == 4 else got, y)
+            if stats is not None:
+                cmp("%s.bn%d.mean" % (key, i + 1), bn.mean.cpu().numpy(), stats[0])
+                cmp("%s.bn%d.std" % (key, i + 1), 1.0 / bn.invstd.cpu().numpy(), stats[1])
+    nodes = chain_nodes(fw["x_fake"])
+    convs = [n for n in nodes if isinstance(n, F.ConvolutionND)]
+    bns = [n for n in nodes if isinstance(n, F.BNActNoise)]
+    assert len(convs) == 5 and len(bns) == 5, [type(n).__name__ for n in nodes]
+    acts = trace["cache_g"]["acts"]
+    for i, cv in enumerate(convs):
+        x = acts[i][0]
+        cmp("G.dc%d.in" % (i + 1), logical(cv.xp)[:, :x.shape[1], 0], x)       # dc1: latent zero-padded 60 -> 64 channels
+    for i, bn in enumerate(bns):
+        y, stats = acts[i][1], acts[i][2]
+        cmp("G.dc%d.out" % (i + 1), logical(bn.yp)[:, :, 0], y)
+        if stats is not None:
+            cmp("G.bn%d.mean" % (i + 1), bn.mean.cpu().numpy(), stats[0])
+            cmp("G.bn%d.std" % (i + 1), 1.0 / bn.invstd.cpu().numpy(), stats[1])
+    if report is not None:
+        report.setdefault("forward", []).append(errs)
+    bad = {k: v for k, v in errs.items() if not v < tol * FORWARD_SLACK.get(k, 1.0)}
+    assert not bad, ("forward tensors beyond %g" % tol, bad)
+    return errs
+
+
+# bf16 whole-step gradients, element-wise max|g - g_ref| / max|g_ref| per parameter group.  Measured on B200 over the
+# bf16 cases of this file (profiles/r02_parity_report.json lists every tensor); the bound is that plus margin.
+BF16_GRAD_BOUNDS = {"default": 0.75}
+
+
+def bf16_grad_bound(model_name, k):
+    return BF16_GRAD_BOUNDS.get("%s/%s" % (model_name, k), BF16_GRAD_BOUNDS.get(model_name, BF16_GRAD_BOUNDS["default"]))
+
+
+def dump_report(tag, report):
+    path = os.environ.get("MCG_PARITY_REPORT")
+    if path:
+        data = {}
+        if os.path.exists(path):
+            with open(path) as f:
+                data = json.load(f)
+        data[tag] = report
+        with open(path, "w") as f:
+            json.dump(data, f, indent=1, sort_keys=True)
 
 
 def build_pair(config, n_filters, dtype_mode, seed=3):
@@ -58,15 +167,33 @@ def build_pair(config, n_filters, dtype_mode, seed=3):
 
     up = Updater(model=model, models=(G, Di, Dv), video_length=16, img_size=64, channel=C, dim_zl=oG.dim_zl,
                  tensorboard_writer=None, iterator=_It(),
-                 optimizer={'image_gen': make_opt(G), 'image_dis': make_opt(Di), 'video_dis': make_opt(Dv)}, device=0)
+                 optimizer={'image_gen': make_opt(G), 'image_dis': make_opt(Di), 'video_dis': make_opt(Dv)}, device=0,
+                 keep_forward=True)
     oup = ref.Updater(model, oG, oI, oV)
     return model, (G, Di, Dv), (oG, oI, oV), up, oup
 
 
-def run_step_case(config, n_filters, N, dtype_mode, tol_out, tol_grad, steps=1, ref32=False):
+def run_step_case(config, n_filters, N, dtype_mode, tol_out, tol_grad, steps=1, ref32=False, override=True, tol_fwd=None,
+                  tag=None):
+    """override=False: pass C is compared WITHOUT handing the device's updated discriminator weights to the oracle, so
+    the oracle's pass C runs on the weights its own passes A/B produced (a pass-B -> pass-C ordering bug on the device
+    cannot hide behind the hand-over); tol_grad then has to absorb Adam's amplification of round-off (see below)."""
     from mocogan_chainer_b200 import kernels as K
     from mocogan_chainer_b200 import random as mrandom
     model, (G, Di, Dv), (oG, oI, oV), up, oup = build_pair(config, n_filters, dtype_mode)
+    C = oG.out_channels
+    report = {"config": config, "n_filters": n_filters, "N": N, "dtype": dtype_mode, "grads": []}
+    try:
+        _run_steps(config, n_filters, N, dtype_mode, tol_out, tol_grad, steps, ref32, override, tol_fwd, report, K, mrandom,
+                   model, (G, Di, Dv), (oG, oI, oV), up, oup)
+    finally:
+        dump_report(tag or "%s_nf%d_N%d_%s" % (config, n_filters, N, dtype_mode), report)
+    return up
+
+
+def _run_steps(config, n_filters, N, dtype_mode, tol_out, tol_grad, steps, ref32, override, tol_fwd, report, K, mrandom, model,
+               nets, onets, up, oup):
+    (G, Di, Dv), (oG, oI, oV) = nets, onets
     C = oG.out_channels
     for step in range(steps):
         x_real = np.random.default_rng(1234 + step).uniform(-1, 1, size=(N, C, 16, 64, 64)).astype(np.float32)
@@ -84,6 +211,8 @@ def run_step_case(config, n_filters, N, dtype_mode, tol_out, tol_grad, steps=1, 
         # pass C is judged on identical updated discriminator weights (see oracle.update_core docstring)
         d_override = {key: {path.lstrip("/"): p.data.float().cpu().numpy().astype(np.float64) for path, p in m.namedparams()}
                       for key, m in (("image_dis", Di), ("video_dis", Dv))}
+        if not override:
+            d_override = None
         trace = {}
         trace32 = None
         if dtype_mode == "fp32" and ref32:
@@ -98,7 +227,10 @@ def run_step_case(config, n_filters, N, dtype_mode, tol_out, tol_grad, steps=1, 
             d_override = None
         olosses = oup.update_core(x_real.astype(np.float64), t_real, r, trace=trace, d_override=d_override)
 
+        check_forward(up, trace, oG, tol_fwd if tol_fwd is not None else tol_out, report)
         kink = ref.kink_margin(trace)
+        gerrs = {}
+        report["grads"].append(gerrs)
         for name, oname in (("ImageDiscriminator", "image_dis/loss"), ("VideoDiscriminator", "video_dis/loss"),
                             ("ImageGenerator", "image_gen/loss")):
             got = float(up.losses[name])
@@ -112,6 +244,10 @@ def run_step_case(config, n_filters, N, dtype_mode, tol_out, tol_grad, steps=1, 
                 if k in bn_fed:   # exactly-zero gradient by construction on the device; round-off in the oracle
                     assert np.abs(g).max() == 0.0 and np.abs(g_ref).max() < 1e-9
                     continue
+                gerrs["%s/%s" % (mine.name, k)] = {
+                    "relerr": relerr(g, g_ref),
+                    "l2": float(np.linalg.norm(g - g_ref) / max(np.linalg.norm(g_ref), 1e-30)),
+                    "cos": float((g * g_ref).sum() / (np.linalg.norm(g) * np.linalg.norm(g_ref) + 1e-30))}
                 if dtype_mode == "fp32":
                     # float32 itself limits how well ANY fp32 implementation can follow the float64 truth through
                     # pass C (Adam's m/(sqrt(v)+eps) amplifies 1e-7 gradient differences into the updated D weights):
@@ -138,7 +274,8 @@ def run_step_case(config, n_filters, N, dtype_mode, tol_out, tol_grad, steps=1, 
                         assert np.abs(g - g_ref).max() < 2e-2 or relerr(g, g_ref) < tol_grad, (step, mine.name, k)
                         continue
                     cos = float((g * g_ref).sum() / (np.linalg.norm(g) * np.linalg.norm(g_ref) + 1e-30))
-                    assert cos > 0.95 and relerr(g, g_ref) < tol_grad, (step, mine.name, k, cos, relerr(g, g_ref))
+                    bound = min(tol_grad, bf16_grad_bound(mine.name, k))
+                    assert cos > 0.95 and relerr(g, g_ref) < bound, (step, mine.name, k, cos, relerr(g, g_ref), bound)
             # Adam + WeightDecay: replay the oracle's rule on the device's own gradients from the pre-step weights
             opt = up.get_optimizer({"ImageGenerator": "image_gen", "ImageDiscriminator": "image_dis",
                                     "VideoDiscriminator": "video_dis"}[mine.name])
@@ -163,7 +300,6 @@ def run_step_case(config, n_filters, N, dtype_mode, tol_out, tol_grad, steps=1, 
             for mine, theirs in ((Di, oI), (Dv, oV), (G, oG)):
                 for path, p in mine.namedparams():
                     theirs.params[path.lstrip("/")][...] = p.data.float().cpu().numpy()
-    return up
 
 
 def test_step_fp32_strict_mnist_shape():
@@ -197,6 +333,26 @@ def test_step_bf16_two_steps_infogan():
 def test_step_fp32_full_width():
     """n_filters = 64 (the width BASELINE quotes) on the strict path, reduced batch."""
     run_step_case("mug_normal", 64, 2, "fp32", 1e-5, 1e-4, ref32=True)
+
+
+def test_step_fp32_pass_c_without_weight_handover():
+    """Pass C judged with NO hand-over of the device's updated discriminator weights to the oracle: each side runs pass C
+    on the weights its own passes A and B produced.  Adam with beta1 = 5e-5 moves every discriminator weight by
+    ~alpha * g / (|g| + eps): fp32 round-off on near-zero gradients becomes ~1e-5 weight differences, which pass C's
+    data gradients see — hence 5e-3 here instead of 1e-4; a device that ran pass C on STALE discriminator weights (or
+    before their update finished) misses by ~alpha / |w| ~ 1e-2 .. 1e-1 on the generator's gradients and fails."""
+    run_step_case("mug_normal", 8, 2, "fp32", 1e-5, 5e-3, override=False, tag="mug_normal_nf8_N2_fp32_nohandover")
+
+
+def test_step_bf16_baseline_config2_batch35():
+    """BASELINE config 2 exactly (normal model, n_filters 64, batch 35): the tile shapes pick_tile chooses at N = 35 /
+    B = 560 (the benchmarked instantiations) inside a whole step, against the float64 oracle."""
+    run_step_case("mug_normal", 64, 35, "bf16", 2e-2, 0.75)
+
+
+def test_step_bf16_baseline_config4_infogan_batch35():
+    """BASELINE config 4 (infogan: 7-way discriminator outputs, categorical terms of updater.py:28-37,53-56), batch 35."""
+    run_step_case("mug_infogan", 64, 35, "bf16", 2e-2, 0.75)
 
 
 def test_losses_track_oracle_over_100_steps():

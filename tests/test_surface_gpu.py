@@ -135,3 +135,91 @@ def test_uint8_batch_equals_float_batch():
         losses.append({k: float(v) for k, v in up.losses.items()})
     for k in losses[0]:
         assert abs(losses[0][k] - losses[1][k]) < 1e-6, (k, losses)
+
+
+@pytest.mark.parametrize("dtype_mode,nf,tol", [("fp32", 16, 1e-5), ("bf16", 64, 2e-2)])
+def test_generator_eval_mode_uses_running_statistics(dtype_mode, nf, tol):
+    """§8f rank 1: under chainer.using_config('train', False) — the state util.py:92 `log_tensorboard` runs the
+    generator in — BatchNorm normalises with the RUNNING statistics (F.fixed_batch_normalization) and
+    updates nothing.  Non-trivial statistics are loaded into both sides; the clip is compared with the oracle's
+    `batchnorm_fixed` forward."""
+    from mocogan_chainer_b200 import chainer
+    from mocogan_chainer_b200 import random as mrandom
+    from oracle import mocogan_ref as ref
+    from tests.test_step_gpu import build_pair, relerr
+    _, (G, Di, Dv), (oG, oI, oV), up, _ = build_pair("mug_normal", nf, dtype_mode)
+    rng = np.random.default_rng(21)
+    G.arena()
+    before = {}
+    for path, link, n in G.namedpersistents():
+        if n == "N":
+            continue
+        key = path.lstrip("/")
+        v = (0.3 * rng.standard_normal(oG.persistent[key].shape)) if n == "avg_mean" else rng.uniform(0.5, 2.0, oG.persistent[key].shape)
+        v = v.astype(np.float32)
+        oG.persistent[key] = v.astype(np.float64)
+        getattr(link, n).copy_(torch.from_numpy(v))
+        before[key] = v
+    N = 3
+    r = ref.draw_step_randoms(np.random.default_rng(100), np.random.default_rng(200), oG, oI, oV, N, (N, 3, 16, 64, 64), t=3,
+                              dtype=np.float32)
+    want, _ = oG.forward(N, r["latents"], update_running=False, train=False)
+    mrandom.set_source(mrandom.InjectedRandom(r))
+    with chainer.using_config('train', False), chainer.no_backprop_mode():
+        x, labels = G(N)
+    torch.cuda.synchronize()
+    assert tuple(x.shape) == (16, N, 3, 64, 64)
+    assert relerr(x.data.float().cpu().numpy(), want) < tol
+    for path, link, n in G.namedpersistents():      # eval mode leaves the running statistics alone
+        if n != "N":
+            assert np.array_equal(getattr(link, n).cpu().numpy(), before[path.lstrip("/")])
+    # and it is a different function from the training-mode forward (batch statistics)
+    mrandom.set_source(mrandom.InjectedRandom(r))
+    with chainer.no_backprop_mode():
+        x_train, _ = G(N)
+    assert relerr(x_train.data.float().cpu().numpy(), want) > 10 * tol
+
+
+def test_log_tensorboard_hook_writes_eval_mode_grid_frames(tmp_path):
+    """util.py:89-115: four grid frames ('{:02d}th frame' at np.linspace(0, T, 4, endpoint=False)) and the first clips as
+    frame strips, generated with train = False; the grid equals util.py:30-51 `to_grid` of the uint8 clips."""
+    from mocogan_chainer_b200 import chainer, util
+    from mocogan_chainer_b200 import random as mrandom
+    from mocogan_chainer_b200.model.net import ImageGenerator
+    from oracle import mocogan_ref as ref
+    chainer.config.compute_dtype = "bf16"
+    np.random.seed(0)
+    G = ImageGenerator(50, 10, 6, 3, 64, 16)
+    G.arena()
+    G.bn1.avg_var.fill_(1.0), G.bn2.avg_var.fill_(1.0), G.bn3.avg_var.fill_(1.0), G.bn4.avg_var.fill_(1.0)
+
+    class Rec(object):
+        def __init__(self):
+            self.images = {}
+
+        def add_image(self, tag, img, step):
+            self.images[tag] = (np.asarray(img), step)
+
+    class Up(object):
+        epoch = 7
+
+    rec = Rec()
+    mrandom.set_source(mrandom.DeviceRandom(seed=5, video_length=16))
+    train_before = chainer.config.train
+    util.log_tensorboard(G, 16, 16, rec)(Up())
+    assert chainer.config.train == train_before
+    assert sorted(k for k in rec.images if k.endswith("frame")) == ["00th frame", "04th frame", "08th frame", "12th frame"]
+    assert sorted(k for k in rec.images if k.startswith("video_")) == ["video_%02d" % i for i in range(10)]
+    img, step = rec.images["04th frame"]
+    assert img.shape == (3, 256, 256) and img.dtype == np.uint8 and step == 7
+    assert rec.images["video_03"][0].shape == (3, 64, 16 * 64)
+    # the same latents again (same Philox state and call ids): the written grid frame is to_grid of the uint8 clips
+    mrandom.set_source(mrandom.DeviceRandom(seed=5, video_length=16))
+    videos, grid = util.sample_videos(G, 16, train=False)
+    assert np.array_equal(grid.cpu().numpy(), ref.to_grid(videos.cpu().numpy(), 4))
+    assert np.array_equal(grid[4].cpu().numpy(), img)
+    assert np.array_equal(ref.to_grid(videos.cpu().numpy(), 4)[:, :, :64, 3 * 64:4 * 64], videos[:, 3].cpu().numpy())
+    w = util.ImageLogWriter(tmp_path / "runs")
+    w.add_image("00th frame", img, 1)
+    w.add_scalar("loss:ImageGenerator", 0.5, 1)
+    assert (tmp_path / "runs" / "00th_frame_000001.png").exists() and (tmp_path / "runs" / "scalars.jsonl").exists()
