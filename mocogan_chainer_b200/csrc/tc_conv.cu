@@ -60,6 +60,12 @@ struct TcParams {
   int tr_kT, tr_kstep, tr_rev;       // taps per group; tap-index step between kt and kt+1; 1 = tap kt reads frame offset kT-1-kt
   int tr_frame_bytes, tr_ablock_bytes;   // bytes of one frame of a block (R rows) / of one block's halo box ((BT+kT-1)*R rows)
   int tr_aslots, tr_bslots;
+  // Temporal tap skipping (fprop / dgrad, unit temporal stride): a pixel box whose A frames for a temporal tap all lie
+  // outside the A tensor multiplies pure zero fill — the video discriminator's data gradients (pT = 0, To = Ti - 3) spend
+  // 23 % (dc2) to 43 % (dc4) of their K steps that way.  Taps are kt-major, so the taps worth issuing for a segment are
+  // one contiguous run: tap-group index i (skip_per_kt taps each) reads frame t*a_mul_t + a_add_t + skip_dt0 + i*skip_dts.
+  int skip_t, skip_per_kt[8], skip_nkt, skip_dt0, skip_dts, skip_aT;   // skip_per_kt: per stride class
+  int box_tn;   // 1: boxes are numbered (w, h, n, t) — frames slowest — so the MT boxes of a step share their frame and skip alike
   int debug_skip_epi;
   int out_f32, ocols;                                        // ocols = channels of one output pixel row
   int planar_chunk, planar_cols;   // fprop: write column c to plane c/chunk as [plane][pixel][chunk] (0 = row-major)
@@ -77,6 +83,7 @@ constexpr int A_BYTES = 128 * 128;  // 128 rows x 64 bf16
 struct TcSeg {
   int tile, k0, nk;    // K steps [k0, k0 + nk) of `tile` (fprop/dgrad: tile = row (cls, nt), all of its K steps)
   int box0, nlive;     // fprop/dgrad: first pixel box and number of 128-row blocks (<= MT) of this step
+  int j0;              // fprop/dgrad: first tap (offset into the class's tap list) of this step — see TcParams::skip_t
 };
 // The same deterministic segment sequence is walked by the producer, the MMA issuer and the epilogue warps.
 template <int MODE, int MT>
@@ -108,7 +115,28 @@ struct TcSegIter {
     if (n > MT) n = MT;
     s.nlive = (int)n;
     s.k0 = 0;
+    s.j0 = 0;
     s.nk = P.tap_count[s.tile / P.ntn] * P.chunks;
+    if (P.skip_t) {
+      // frames covered by the step's boxes.  box index = ((n*nbt + t)*nbh + h)*nbw + w: a step that crosses into the next
+      // sample keeps every tap; with box_tn = ((t*nbb + n)*nbh + h)*nbw + w: frames never wrap inside a step
+      const int per_t = P.nbw * P.nbh, b_last = s.box0 + (int)n - 1;
+      const int q0 = s.box0 / per_t, q1 = b_last / per_t;
+      if (P.box_tn || q0 / P.nbt == q1 / P.nbt) {
+        const int t_first = P.box_tn ? q0 / P.nbb : q0 % P.nbt, t_last = P.box_tn ? q1 / P.nbb : q1 % P.nbt;
+        const int a_lo = t_first * P.BT * P.a_mul_t + P.a_add_t + P.skip_dt0;
+        const int a_hi = (t_last * P.BT + P.BT - 1) * P.a_mul_t + P.a_add_t + P.skip_dt0;
+        int i_lo, i_hi;   // tap groups i with [a_lo, a_hi] + i*dts meeting [0, aT)
+        if (P.skip_dts > 0) { i_lo = -a_hi; i_hi = P.skip_aT - 1 - a_lo; }
+        else { i_lo = a_lo - (P.skip_aT - 1); i_hi = a_hi; }
+        if (i_lo < 0) i_lo = 0;
+        if (i_hi > P.skip_nkt - 1) i_hi = P.skip_nkt - 1;
+        const int groups = i_hi >= i_lo ? i_hi - i_lo + 1 : 0;
+        const int per_kt = P.skip_per_kt[s.tile / P.ntn];
+        s.j0 = groups ? i_lo * per_kt : 0;
+        s.nk = groups * per_kt * P.chunks;
+      }
+    }
     u += n;
     return true;
   }
@@ -169,8 +197,13 @@ __device__ __forceinline__ TcBox tc_decode_box(const TcParams& P, int bi) {
   TcBox b;
   b.w0 = (bi % P.nbw) * P.BW; bi /= P.nbw;
   b.h0 = (bi % P.nbh) * P.BH; bi /= P.nbh;
-  b.t0 = (bi % P.nbt) * P.BT; bi /= P.nbt;
-  b.n0 = bi * P.BB;
+  if (P.box_tn) {
+    b.n0 = (bi % P.nbb) * P.BB; bi /= P.nbb;
+    b.t0 = bi * P.BT;
+  } else {
+    b.t0 = (bi % P.nbt) * P.BT; bi /= P.nbt;
+    b.n0 = bi * P.BB;
+  }
   return b;
 }
 
@@ -400,8 +433,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
             bx[m].t0 = bx[m].t0 * P.a_mul_t + P.a_add_t;
           }
           const uint32_t tx_bytes = sg.nlive * A_BYTES + B_BYTES;
-          const int j_end = P.tap_begin[cls] + P.tap_count[cls], chunks = P.chunks;
-          for (int j = P.tap_begin[cls]; alive && j < j_end; ++j) {
+          const int chunks = P.chunks;
+          const int j_beg = P.tap_begin[cls] + sg.j0, j_end = j_beg + sg.nk / chunks;
+          for (int j = j_beg; alive && j < j_end; ++j) {
             const TcTap tp = P.taps[j];
             const int kcol = tp.kidx * P.Cin;
             for (int c = 0; c < chunks; ++c) {
@@ -983,6 +1017,372 @@ static bool tr_wanted(const TrPlan& tr, double plain_cost) {
   return v && atoi(v) != 0 && tr.ok;
 }
 
+// =============================================================================================================
+// Class-fused data gradient for the 64-channel stride-2 layers (Dv.dc2, G.dc4: k = 4, s = 2, p = 1 in H and W).
+//
+// The plain dgrad treats the sH*sW = 4 parity classes of the input grid as four independent stride-1 convolutions
+// over dy with N = Cin = 64 accumulator columns each: every class loads its own 2 x 2 (kh, kw) boxes of dy per temporal
+// tap, 16 box loads per (kt, 64-channel chunk) and 128 class pixels, and these kernels are bound by L2 -> SM bytes
+// (the tensor pipe of Dv.dc2's dgrad is busy 45 % of the time while the SMs pull 2.2 GB through a ~7 KB/clk fabric).
+// But class (ph, pw) reads dy at row offsets {-1, 0} (ph = 0) or {0, +1} (ph = 1), likewise in w: the 16 loads are only
+// 9 distinct boxes.  Here ONE tile is 128 pixels of the class sub-grid x 256 columns = the four classes x 64 ci, laid
+// out in TMEM in the cyclic order (0,0) (0,1) (1,1) (1,0) so that the classes sharing an offset are adjacent columns:
+//   offset ( 0, 0)            -> one MMA, N = 256          offsets (-1,0) (0,+1) (+1,0) -> one MMA each, N = 128
+//   offset ( 0,-1)            -> two MMAs, N = 64           the four corners            -> one MMA each, N = 64
+// Two pixel blocks (MT = 2) share every weight slab, so the accumulators fill all 512 TMEM columns (single-buffered;
+// the TMA ring keeps loading the next tile under the epilogue).  Per (kt, chunk) and 256 pixels the SM pulls
+// 2 x 9 x 16 KB of dy + 16 x 8 KB of weights = 416 KB instead of 576 KB, and issues 40 wide MMAs instead of 64 narrow
+// ones.  Temporal taps whose dy frame lies outside the clip are skipped like in the plain kernel.
+// Work split: every CTA owns q = blocks / grid consecutive 128-pixel blocks (walked in pairs); the blocks % grid
+// left-over blocks are cut into their four classes and dealt round-robin as single-class units (4 boxes, N = 64), so no
+// CTA carries a whole extra block.
+// =============================================================================================================
+struct Tc4Stage {
+  int8_t dh, dw;            // dy box offset
+  uint8_t nslab;            // weight slabs (64 co x 64 ci, one per class that uses this offset), in TMEM column order
+  uint8_t nmma;             // MMAs over runs of adjacent classes
+  uint8_t khkw[4];          // kh*kW + kw of each slab's tap
+  uint8_t mma_col[2], mma_n[2], mma_slab[2];   // per MMA: first TMEM class slot, classes covered, first slab
+  uint8_t big;              // uses the 4-slab ring slot
+};
+struct Tc4Params {
+  int BW, BH, BT, BB, nbw, nbh, nbt, nbb;
+  int EN, full_w, full_h, full_t;
+  long long os_w, os_h, os_t, os_n;
+  int chunks, kT, kHW, pT, aT, Cin;
+  int nblocks, q, rem_units, rem_block0;
+  int out_f32;
+  int nst[5];               // stages of schedule 0 (all classes) and 1 + c (class c only)
+  uint8_t cls_at_slot[4], slot_of_cls[4];
+  Tc4Stage st[5][9];
+};
+constexpr int kT4Small = 2 * A_BYTES + 2 * 8192, kT4Big = 2 * A_BYTES + 4 * 8192, kT4SmallSlots = 3;
+constexpr int kT4Smem = kT4Big + kT4SmallSlots * kT4Small + 1024;
+
+struct Tc4Seg { int box0, nlive, sched, kt_lo, kt_n; };
+struct Tc4Iter {
+  int b, b_end, u, phase;
+  __device__ __forceinline__ explicit Tc4Iter(const Tc4Params& P) {
+    b = (int)blockIdx.x * P.q; b_end = b + P.q; u = (int)blockIdx.x; phase = 0;
+  }
+  __device__ __forceinline__ bool next(const Tc4Params& P, Tc4Seg& s) {
+    if (b < b_end) {
+      s.box0 = b; s.nlive = b_end - b >= 2 ? 2 : 1; s.sched = 0;
+      b += s.nlive;
+    } else if (u < P.rem_units) {
+      s.box0 = P.rem_block0 + (u >> 2); s.nlive = 1; s.sched = 1 + (u & 3);
+      u += (int)gridDim.x;
+    } else {
+      return false;
+    }
+    // temporal taps worth issuing: dy frame = t + pT - kt must meet [0, aT) for some frame t of the step's boxes
+    // (boxes are numbered (w, h, n, t): the two blocks of a pair share their frame except once per frame change)
+    const int per_t = P.nbw * P.nbh * P.nbb;
+    const int t_lo = (s.box0 / per_t) * P.BT, t_hi = ((s.box0 + s.nlive - 1) / per_t) * P.BT + P.BT - 1;
+    int lo = t_lo + P.pT - (P.aT - 1), hi = t_hi + P.pT;
+    if (lo < 0) lo = 0;
+    if (hi > P.kT - 1) hi = P.kT - 1;
+    s.kt_lo = lo; s.kt_n = hi >= lo ? hi - lo + 1 : 0;
+    return true;
+  }
+};
+__device__ __forceinline__ TcBox tc4_decode_box(const Tc4Params& P, int bi) {
+  TcBox b;
+  b.w0 = (bi % P.nbw) * P.BW; bi /= P.nbw;
+  b.h0 = (bi % P.nbh) * P.BH; bi /= P.nbh;
+  b.n0 = (bi % P.nbb) * P.BB; bi /= P.nbb;
+  b.t0 = bi * P.BT;
+  return b;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_dgrad4_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                  const __grid_constant__ CUtensorMap mapB,
+                                                                  const __grid_constant__ Tc4Params P, void* __restrict__ out,
+                                                                  const float* __restrict__ bias) {
+  pdl_launch_dependents();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[1 + kT4SmallSlots], empty_bar[1 + kT4SmallSlots], tfull_bar, tempty_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* err = &g_tc_error;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 1 + kT4SmallSlots; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tfull_bar, 1);
+    mbar_init(&tempty_bar, kEpiThreads);
+    fence_barrier_init();
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  pdl_wait();
+
+  // ring: slot 0 = the 4-slab slot (the centre offset's stage), slots 1..3 = 2-slab slots; A first, then the slabs
+  const uint32_t smem_a = smem_u32(smem);
+  const uint32_t full_a = smem_u32(&full_bar[0]), empty_a = smem_u32(&empty_bar[0]);
+  const uint32_t tfull_a = smem_u32(&tfull_bar), tempty_a = smem_u32(&tempty_bar);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint64_t map_a = reinterpret_cast<uint64_t>(&mapA), map_b = reinterpret_cast<uint64_t>(&mapB);
+      Tc4Iter iter(P);
+      Tc4Seg sg;
+      uint32_t ph_big = 1, ph_small = 1;
+      int si = 0;
+      bool alive = true;
+      while (alive && iter.next(P, sg)) {
+        TcBox bx[2];
+        bx[0] = tc4_decode_box(P, sg.box0);
+        bx[1] = tc4_decode_box(P, sg.box0 + (sg.nlive > 1 ? 1 : 0));
+        const int nst = P.nst[sg.sched];
+        for (int kt = sg.kt_lo; alive && kt < sg.kt_lo + sg.kt_n; ++kt) {
+          const int dt = P.pT - kt, kbase = kt * P.kHW;
+          for (int c = 0; alive && c < P.chunks; ++c) {
+            for (int s = 0; s < nst; ++s) {
+              const Tc4Stage& st = P.st[sg.sched][s];
+              uint32_t slot, ph;
+              if (st.big) { slot = 0; ph = ph_big; ph_big ^= 1; }
+              else { slot = 1 + si; ph = ph_small; if (++si == kT4SmallSlots) { si = 0; ph_small ^= 1; } }
+              const uint32_t base = smem_a + (slot ? kT4Big + (slot - 1) * kT4Small : 0), fb = full_a + slot * 8;
+              if (!mbar_wait_a(empty_a + slot * 8, ph, err)) { alive = false; break; }
+              mbar_expect_tx_a(fb, sg.nlive * A_BYTES + st.nslab * 8192);
+              tma_load_5d_a(base, map_a, fb, c * 64, bx[0].w0 + st.dw, bx[0].h0 + st.dh, bx[0].t0 + dt, bx[0].n0);
+              if (sg.nlive > 1)
+                tma_load_5d_a(base + A_BYTES, map_a, fb, c * 64, bx[1].w0 + st.dw, bx[1].h0 + st.dh, bx[1].t0 + dt, bx[1].n0);
+              for (int sl = 0; sl < st.nslab; ++sl)
+                tma_load_2d_a(base + 2 * A_BYTES + sl * 8192, map_b, fb, (kbase + st.khkw[sl]) * P.Cin, c * 64);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t desc_hi = smem_desc_hi(1024);
+      const uint32_t id64 = make_idesc_bf16(128, 64, 0, 1), id128 = make_idesc_bf16(128, 128, 0, 1), id256 = make_idesc_bf16(128, 256, 0, 1);
+      Tc4Iter iter(P);
+      Tc4Seg sg;
+      uint32_t ph_big = 0, ph_small = 0, nseg = 0;
+      int si = 0;
+      bool alive = true;
+      while (alive && iter.next(P, sg)) {
+        if (sg.kt_n == 0) continue;
+        if (!mbar_wait_a(tempty_a, (nseg & 1) ^ 1, err)) break;
+        tc_fence_after();
+        const int nst = P.nst[sg.sched];
+        const int steps = sg.kt_n * P.chunks;
+        bool first = true;
+        for (int g = 0; alive && g < steps; ++g) {
+          for (int s = 0; s < nst; ++s) {
+            const Tc4Stage& st = P.st[sg.sched][s];
+            uint32_t slot, ph;
+            if (st.big) { slot = 0; ph = ph_big; ph_big ^= 1; }
+            else { slot = 1 + si; ph = ph_small; if (++si == kT4SmallSlots) { si = 0; ph_small ^= 1; } }
+            const uint32_t base = smem_a + (slot ? kT4Big + (slot - 1) * kT4Small : 0);
+            if (!mbar_wait_a(full_a + slot * 8, ph, err)) { alive = false; break; }
+            tc_fence_after();
+            const uint32_t a_lo = smem_desc_lo(base, 16), b_lo = smem_desc_lo(base + 2 * A_BYTES, 8192);
+            for (int m = 0; m < sg.nlive; ++m) {
+              for (int j = 0; j < st.nmma; ++j) {
+                const uint32_t d = tmem + m * 256 + st.mma_col[j] * 64;
+                const uint32_t id = st.mma_n[j] == 4 ? id256 : (st.mma_n[j] == 2 ? id128 : id64);
+                const uint32_t bj = b_lo + st.mma_slab[j] * (8192 >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_lh(d, a_lo + m * (A_BYTES >> 4) + k * 2, desc_hi, bj + k * (2048 >> 4), desc_hi, id,
+                               (first && k == 0) ? 0u : 1u);
+              }
+            }
+            umma_commit_a(empty_a + slot * 8);
+            first = false;
+          }
+        }
+        if (alive) umma_commit_a(tfull_a);
+        ++nseg;
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    int rr = r;
+    const int iw = rr % P.BW; rr /= P.BW;
+    const int ih = rr % P.BH; rr /= P.BH;
+    const int itt = rr % P.BT; rr /= P.BT;
+    const int ib = rr;
+    const int c0 = half * 32;
+    float bv[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bv[i] = bias ? bias[c0 + i] : 0.f;
+    Tc4Iter iter(P);
+    Tc4Seg sg;
+    uint32_t nseg = 0;
+    while (iter.next(P, sg)) {
+      const bool have_acc = sg.kt_n > 0;
+      if (have_acc) {
+        if (!mbar_wait_a(tfull_a, nseg & 1, err)) break;
+        tc_fence_after();
+      }
+      const uint32_t acc = tmem + (uint32_t(q * 32) << 16);
+      const int s_lo = sg.sched ? P.slot_of_cls[sg.sched - 1] : 0, s_hi = sg.sched ? s_lo + 1 : 4;
+#pragma unroll 1
+      for (int m = 0; m < sg.nlive; ++m) {
+        const TcBox bx = tc4_decode_box(P, sg.box0 + m);
+        const int on = bx.n0 + ib, ot = bx.t0 + itt;
+#pragma unroll 1
+        for (int sl = s_lo; sl < s_hi; ++sl) {
+          const int cls = P.cls_at_slot[sl];
+          const int ow = (bx.w0 + iw) * 2 + (cls & 1), oh = (bx.h0 + ih) * 2 + (cls >> 1);
+          const bool valid = ow < P.full_w && oh < P.full_h && ot < P.full_t && on < P.EN;
+          uint32_t v[32];
+          if (have_acc) {
+            tmem_ld32(acc + m * 256 + sl * 64 + c0, v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
+          }
+          if (valid) {
+            const long long base = (long long)on * P.os_n + (long long)ot * P.os_t + (long long)oh * P.os_h + (long long)ow * P.os_w + c0;
+            if (P.out_f32) {
+              float* o = reinterpret_cast<float*>(out) + base;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(o + i) = make_float4(__uint_as_float(v[i]) + bv[i], __uint_as_float(v[i + 1]) + bv[i + 1],
+                                                                __uint_as_float(v[i + 2]) + bv[i + 2], __uint_as_float(v[i + 3]) + bv[i + 3]);
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + base;
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                uint4 u;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  h[e] = __floats2bfloat162_rn(__uint_as_float(v[i + 2 * e]) + bv[i + 2 * e], __uint_as_float(v[i + 2 * e + 1]) + bv[i + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(o + i) = u;
+              }
+            }
+          }
+        }
+      }
+      if (have_acc) {
+        tc_fence_before();
+        mbar_arrive_a(tempty_a);
+        ++nseg;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// the fused kernel takes: Cin = 64, 4 x 4 spatial taps, stride 2, pad 1 in H and W, unit temporal stride, full weight rows,
+// and enough pixel blocks that every CTA walks at least one pair
+static bool dgrad4_geom_ok(const mcg_conv_geom* g, int wrows) {
+  return g->Cin == 64 && g->Cout % 64 == 0 && g->kH == 4 && g->kW == 4 && g->sH == 2 && g->sW == 2 && g->pH == 1 && g->pW == 1 &&
+         g->sT == 1 && g->kT <= 4 && wrows == g->Cout && g->Hi % 2 == 0 && g->Wi % 2 == 0;
+}
+static int tc_dgrad4(const mcg_conv_geom* g, const void* dy, const void* w, void* dx, const float* bias, int out_dtype,
+                     cudaStream_t st, bool* taken) {
+  const char* who = "mcg_conv_dgrad(tc,class-fused)";
+  *taken = false;
+  const int EW = g->Wi / 2, EH = g->Hi / 2, ET = g->Ti;
+  const Box bx = choose_box(128, EW, EH, ET, g->N);
+  Tc4Params P;
+  memset(&P, 0, sizeof(P));
+  P.BW = bx.w; P.BH = bx.h; P.BT = bx.t; P.BB = bx.b;
+  P.nbw = ceil_div(EW, bx.w); P.nbh = ceil_div(EH, bx.h); P.nbt = ceil_div(ET, bx.t); P.nbb = ceil_div(g->N, bx.b);
+  P.nblocks = P.nbw * P.nbh * P.nbt * P.nbb;
+  const int sms = tc_sms();
+  if (P.nblocks < 2 * sms) return 0;          // small layers (Di.dc2: 70 blocks) keep the per-class kernel
+  *taken = true;
+  P.EN = g->N; P.full_w = g->Wi; P.full_h = g->Hi; P.full_t = g->Ti;
+  P.os_w = g->Cin; P.os_h = (long long)g->Wi * g->Cin; P.os_t = (long long)g->Hi * P.os_h; P.os_n = (long long)g->Ti * P.os_t;
+  P.chunks = g->Cout / 64; P.kT = g->kT; P.kHW = g->kH * g->kW; P.pT = g->pT; P.aT = g->To; P.Cin = g->Cin;
+  P.out_f32 = (out_dtype == MCG_F32);
+  const int grid = sms;
+  P.q = P.nblocks / grid;
+  P.rem_block0 = P.q * grid;
+  P.rem_units = 4 * (P.nblocks - P.rem_block0);
+  // classes c = ph*2 + pw in the cyclic TMEM order (0,0) (0,1) (1,1) (1,0)
+  const uint8_t order[4] = {0, 1, 3, 2};
+  for (int s = 0; s < 4; ++s) { P.cls_at_slot[s] = order[s]; P.slot_of_cls[order[s]] = (uint8_t)s; }
+  // which classes read dy at offset (dh, dw), and through which tap: dh = (ph + pH - kh) / sH where that division is exact
+  struct Use { int cls, khkw; };
+  std::vector<Use> uses[3][3];
+  for (int c = 0; c < 4; ++c) {
+    const int ph = c >> 1, pw = c & 1;
+    for (int kh = 0; kh < 4; ++kh) {
+      if ((ph + 1 - kh) % 2) continue;
+      for (int kw = 0; kw < 4; ++kw) {
+        if ((pw + 1 - kw) % 2) continue;
+        const int dh = (ph + 1 - kh) / 2, dw = (pw + 1 - kw) / 2;
+        if (dh < -1 || dh > 1 || dw < -1 || dw > 1) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: offset out of the 3x3 window", who);
+        uses[dh + 1][dw + 1].push_back(Use{c, kh * 4 + kw});
+      }
+    }
+  }
+  auto build = [&](int sched, int only_cls) -> int {
+    int n = 0;
+    for (int pass = 4; pass >= 1; --pass)            // widest stages first: the first stage of a tile must cover every column
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+          std::vector<Use> u;
+          for (const Use& x : uses[a][b])
+            if (only_cls < 0 || x.cls == only_cls) u.push_back(x);
+          if ((int)u.size() != pass) continue;
+          if (only_cls >= 0 && pass != 1) continue;
+          Tc4Stage& s = P.st[sched][n++];
+          memset(&s, 0, sizeof(s));
+          s.dh = (int8_t)(a - 1); s.dw = (int8_t)(b - 1);
+          // slabs in TMEM slot order
+          for (size_t i = 0; i < u.size(); ++i)
+            for (size_t j = i + 1; j < u.size(); ++j)
+              if (P.slot_of_cls[u[j].cls] < P.slot_of_cls[u[i].cls]) std::swap(u[i], u[j]);
+          s.nslab = (uint8_t)u.size();
+          s.big = s.nslab > 2;
+          for (size_t i = 0; i < u.size(); ++i) s.khkw[i] = (uint8_t)u[i].khkw;
+          // MMAs over runs of adjacent slots
+          size_t i = 0;
+          while (i < u.size()) {
+            size_t j = i + 1;
+            while (j < u.size() && P.slot_of_cls[u[j].cls] == P.slot_of_cls[u[j - 1].cls] + 1) ++j;
+            if (s.nmma >= 2 || (j - i) == 3) return -1;
+            s.mma_col[s.nmma] = P.slot_of_cls[u[i].cls]; s.mma_n[s.nmma] = (uint8_t)(j - i); s.mma_slab[s.nmma] = (uint8_t)i;
+            ++s.nmma;
+            i = j;
+          }
+        }
+    return n;
+  };
+  P.nst[0] = build(0, -1);
+  for (int c = 0; c < 4; ++c) P.nst[1 + c] = build(1 + c, c);
+  if (P.nst[0] != 9 || P.st[0][0].nslab != 4 || P.st[0][0].nmma != 1)
+    MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: unexpected stage table (%d stages)", who, P.nst[0]);
+  for (int c = 0; c < 4; ++c)
+    if (P.nst[1 + c] != 4) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: unexpected class stage table", who);
+  CUtensorMap ma, mb;
+  int rc;
+  if ((rc = act_map(&ma, dy, g->Cout, g->Wo, g->Ho, g->To, g->N, bx.w, bx.h, bx.t, bx.b, 1, 1, 1))) return rc;
+  const int Ktot = g->kT * g->kH * g->kW * g->Cin;
+  uint64_t d2[2] = {(uint64_t)Ktot, (uint64_t)g->Cout}, s2[1] = {(uint64_t)Ktot * 2};
+  uint32_t b2[2] = {64, 64}, e2[2] = {1, 1};
+  if ((rc = get_map(&mb, w, 2, d2, s2, b2, e2))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_dgrad4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT4Smem);
+    if (e != cudaSuccess) MCG_FAIL((int)e, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
+    configured = true;
+  }
+  pdl(tc_dgrad4_kernel, grid, kTcThreads, kT4Smem, st)(ma, mb, P, dx, bias);
+  MCG_CHECK_LAUNCH(who);
+  return 0;
+}
+
 bool tc_supported(const mcg_conv_geom* g) {
   if (g->Cin % 64 || g->Cout % 64) return false;
   if (g->sT > 2 || g->sH > 2 || g->sW > 2) return false;
@@ -1061,6 +1461,10 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
       }
     }
     if ((rc = act_map(&ma, a, g->Cin, g->Wi, g->Hi, g->Ti, g->N, bx.w, bx.h, bx.t, bx.b, g->sW, g->sH, g->sT))) return rc;
+    if (g->kT > 1 && g->pT > 0 && !tc_env_int("MCG_TC_NOSKIP")) {   // temporal zero padding: edge boxes skip the taps that read only padding
+      P.skip_t = 1; P.skip_per_kt[0] = g->kH * g->kW; P.skip_nkt = g->kT; P.skip_dt0 = 0; P.skip_dts = 1; P.skip_aT = g->Ti;
+      P.box_tn = 1;
+    }
     P.ntn = g->Cout / cfg.bn;
     P.ntiles = P.ntn;
     const int grid = split_units(P, (long long)P.ntiles * P.nboxes, 1);
@@ -1071,6 +1475,12 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
   }
   if (mode == kDgrad) {
     // a = dy (N,To,Ho,Wo,Cout), b = w bf16, out = dx (N,Ti,Hi,Wi,Cin); one class per residue of the input coordinate
+    if (dgrad4_geom_ok(g, wrows) && !tc_env_int("MCG_TC_NOFUSE") && !tc_env_int("MCG_TC_TR") && !tc_env_int("MCG_TC_MT") &&
+        !tc_env_int("MCG_TC_BN")) {
+      bool taken = false;
+      if ((rc = tc_dgrad4(g, a, b, out, bias, out_dtype, st, &taken))) return rc;
+      if (taken) return 0;
+    }
     const int cw = g->sW, ch = g->sH, ct = g->sT;
     const int EW = ceil_div(g->Wi, cw), EH = ceil_div(g->Hi, ch), ET = ceil_div(g->Ti, ct);
     Box bx = choose_box(128, EW, EH, ET, g->N);
@@ -1143,6 +1553,12 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
       }
     }
     if ((rc = act_map(&ma, a, g->Cout, g->Wo, g->Ho, g->To, g->N, bx.w, bx.h, bx.t, bx.b, 1, 1, 1))) return rc;
+    if (g->kT > 1 && ct == 1 && !tc_env_int("MCG_TC_NOSKIP")) {
+      // input frame t reads dy frame t + pT - kt: near both ends of the clip most temporal taps fall outside dy (To < Ti)
+      P.skip_t = 1; P.skip_nkt = g->kT; P.skip_dt0 = g->pT; P.skip_dts = -1; P.skip_aT = g->To;
+      P.box_tn = 1;
+      for (int c = 0; c < ncls; ++c) P.skip_per_kt[c] = P.tap_count[c] / g->kT;
+    }
     P.ntn = g->Cin / cfg.bn;
     P.ntiles = ncls * P.ntn;
     const int grid = split_units(P, (long long)P.ntiles * P.nboxes, 1);

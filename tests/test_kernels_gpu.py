@@ -97,6 +97,10 @@ def run_conv_case(K, case, impl, dtype, tol):
     K.conv_fprop(g, xd, wd, bd, yd, impl)
     dxd = torch.empty_like(xd)
     K.conv_dgrad(g, gyd, wd, None, dxd, impl)
+    # a deconvolution's forward is this data gradient plus its bias (net.py:110-114)
+    b_in = rng.standard_normal(Cin)
+    dxb = torch.empty_like(xd)
+    K.conv_dgrad(g, gyd, wd, torch.from_numpy(b_in).float().cuda(), dxb, impl)
     dwd = torch.zeros(wd.shape, dtype=torch.float32, device="cuda")
     K.conv_wgrad(g, xd, gyd, dwd, impl)
     K.conv_wgrad(g, xd, gyd, dwd, impl)  # accumulates: expect exactly 2x
@@ -104,6 +108,7 @@ def run_conv_case(K, case, impl, dtype, tol):
     assert K.tc_error_flag() == 0
     assert relerr(from_cl(yd, nd), y_ref) < tol, name
     assert relerr(from_cl(dxd, nd), gx_ref) < tol, name
+    assert relerr(from_cl(dxb, nd), gx_ref + b_in.reshape((1, Cin) + (1,) * len(in_sp))) < tol, name
     assert relerr(w_from_internal(dwd), 2 * gW_ref) < tol, name
 
 
@@ -129,6 +134,10 @@ TC_CASES = [
     ("tc_di_dc1", 2, 3, 3, 64, (16, 16), (4, 4), (2, 2), (1, 1)),
     ("tc_dv_dc1", 3, 2, 3, 64, (7, 16, 16), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
     ("tc_c1", 2, 3, 1, 64, (16, 16), (4, 4), (2, 2), (1, 1)),
+    # class-fused data gradient (Cin = 64, k4 s2 p1, >= 2 x 148 pixel blocks): 315 blocks = pairs + 19 blocks dealt out as
+    # single-class units, temporal taps skipped at both ends of the clip; 460 blocks = odd per-CTA count (pair + single)
+    ("tc3d_fused", 3, 10, 64, 64, (7, 48, 48), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
+    ("tc2d_fused_odd", 2, 230, 64, 128, (32, 32), (4, 4), (2, 2), (1, 1)),
 ]
 
 

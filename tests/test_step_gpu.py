@@ -110,13 +110,18 @@ def check_forward(up, trace, oG, tol, report=None):
     return errs
 
 
-# bf16 whole-step gradients, element-wise max|g - g_ref| / max|g_ref| per parameter group.  Measured on B200 over the
-# bf16 cases of this file (profiles/r02_parity_report.json lists every tensor); the bound is that plus margin.
-BF16_GRAD_BOUNDS = {"default": 0.75}
-
-
-def bf16_grad_bound(model_name, k):
-    return BF16_GRAD_BOUNDS.get("%s/%s" % (model_name, k), BF16_GRAD_BOUNDS.get(model_name, BF16_GRAD_BOUNDS["default"]))
+# bf16 whole-step gradients.  What was measured on B200 over the bf16 cases of this file (every tensor is listed in
+# profiles/r02_parity_report.json), worst case per network as (max|g - g_ref| / max|g_ref|, L2 relative error, cosine):
+#   ImageGenerator      0.49  0.24  0.972     (g0/*, dc1/W worst: the end of the longest chain, ~20 bf16 tensors deep)
+#   ImageDiscriminator  0.35  0.14  0.992     (dc5/b, one element, is judged absolutely: a difference of two ~0.5/N terms)
+#   VideoDiscriminator  0.28  0.16  0.988
+# Only the last layers (dc5/W, bn4/gamma: 1e-2) stay inside the per-layer 2e-2: every earlier gradient has passed through
+# BatchNorm backward's gy - mean(gy) - xhat*mean(gy*xhat), which cancels most of gy and leaves bf16's 2^-9 storage rounding
+# of gy (and the (Leaky)ReLU masks flipped by the rounded forward activations) as a 5-25 % L2 perturbation — the
+# discriminator losses back-propagate from ONE sample (updater.py:25-26), so nothing averages it out.  The bounds are the
+# measured worst case with ~1.4x margin; the <= 2e-2 per-layer bound on identical inputs lives in test_kernels_gpu.py.
+BF16_GRAD_BOUNDS = {"ImageGenerator": (0.70, 0.33), "ImageDiscriminator": (0.50, 0.20), "VideoDiscriminator": (0.40, 0.22)}
+BF16_GRAD_COS = 0.96
 
 
 def dump_report(tag, report):
@@ -274,8 +279,10 @@ def _run_steps(config, n_filters, N, dtype_mode, tol_out, tol_grad, steps, ref32
                         assert np.abs(g - g_ref).max() < 2e-2 or relerr(g, g_ref) < tol_grad, (step, mine.name, k)
                         continue
                     cos = float((g * g_ref).sum() / (np.linalg.norm(g) * np.linalg.norm(g_ref) + 1e-30))
-                    bound = min(tol_grad, bf16_grad_bound(mine.name, k))
-                    assert cos > 0.95 and relerr(g, g_ref) < bound, (step, mine.name, k, cos, relerr(g, g_ref), bound)
+                    l2 = float(np.linalg.norm(g - g_ref) / max(np.linalg.norm(g_ref), 1e-30))
+                    bmax, bl2 = BF16_GRAD_BOUNDS[mine.name]
+                    assert cos > BF16_GRAD_COS and relerr(g, g_ref) < min(tol_grad, bmax) and l2 < bl2, \
+                        (step, mine.name, k, cos, relerr(g, g_ref), l2)
             # Adam + WeightDecay: replay the oracle's rule on the device's own gradients from the pre-step weights
             opt = up.get_optimizer({"ImageGenerator": "image_gen", "ImageDiscriminator": "image_dis",
                                     "VideoDiscriminator": "video_dis"}[mine.name])
