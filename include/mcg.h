@@ -76,7 +76,10 @@ int mcg_conv_wgrad(const mcg_conv_geom* g, const void* x, const void* dy, float*
  *   path): mean, biased var; writes mean[C], invstd[C] = 1/sqrt(var+eps), and the fused affine
  *   scale[C] = gamma*invstd, shift[C] = beta - mean*scale; updates running stats in place when non-NULL:
  *   avg_mean = decay*avg_mean + (1-decay)*mean; avg_var = decay*avg_var + (1-decay)*m/max(m-1,1)*(var+eps).
- * workspace: mcg_colreduce_workspace_bytes(M, C).                                                        */
+ * workspace: mcg_colreduce_workspace_bytes(M, C) bytes that the caller ZERO-FILLS ONCE, when it allocates them, and
+ *   reuses for every call of this group on the same stream: each reduction is ONE kernel — the blocks add their column
+ *   sums into 16 slot rows, and the block that draws the last ticket finalises (statistics / sums -> outputs) and
+ *   leaves slots and ticket counter zeroed again.  Summation order across blocks is not fixed (fp32 red.add).     */
 size_t mcg_colreduce_workspace_bytes(long long M, int C);
 int mcg_bn_stats(const void* y, long long M, int C, int dtype, const float* gamma, const float* beta, float eps,
                  float decay, float* mean, float* invstd, float* scale, float* shift, float* avg_mean,
@@ -159,6 +162,12 @@ int mcg_loss_gen(const float* y_i, const float* y_v, const int* t_fake, int N, i
 int mcg_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float alpha, float beta1,
                   float beta2, float eps, float wd, float grad_scale, const int* t_ptr, void* stream);
 int mcg_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+/* Link.cleargrads (Chainer: optimizer.update -> target.cleargrads, updater.py:111-113): the flat gradient buffer of a
+ * model is zero-filled on the stream (cudaMemsetAsync: a memset node in a captured step, no kernel).           */
+int mcg_fill_zero(void* p, size_t bytes, void* stream);
+/* dst[row][0..Cp) = src[row][0..C), zeros beyond: the generator's latent z (net.py:106-107, 60 = dim_zc + dim_zm
+ * channels) padded to the 64 channels the tcgen05 path needs (see MCG_W_ROWS).                                  */
+int mcg_pad_channels(const void* src, void* dst, long long rows, int C, int Cp, int dtype, void* stream);
 
 /* ---- device-side step state (RNG key, step counter, frame index) so a captured step replays fresh -------
  * state layout (8 x uint32): seed_lo, seed_hi, step, frame_t, adam_t, reserved[3].

@@ -478,7 +478,7 @@ class Link(object):
     def cleargrads(self):
         """Chainer sets grads to None and lets backward allocate; here the gradient arena is zero-filled (one
         memset) because the wgrad kernels accumulate in place."""
-        self.arena().grad.zero_()
+        K.fill_zero(self.arena().grad)
 
     zerograds = cleargrads
 

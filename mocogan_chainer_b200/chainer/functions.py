@@ -199,8 +199,8 @@ class ConvolutionND(FunctionNode):
             Cp = (Cx + 63) // 64 * 64
             gp = K.make_geom(N, ish[-1], Cp, in_sp, k, s, p)
             if K.tc_ok(gp):
-                xpad = torch.zeros((N, T, H, Wd, Cp), dtype=xp.dtype, device=xp.device)
-                xpad[..., :Cx].copy_(xp)
+                xpad = torch.empty((N, T, H, Wd, Cp), dtype=xp.dtype, device=xp.device)
+                K.pad_channels(xp.contiguous(), xpad)
                 xp, g, self.w_rows = xpad, gp, Cx
         self.g = g
         self.impl = K.IMPL_TC if (config.compute_dtype == "bf16" and xp.dtype == torch.bfloat16 and K.tc_ok(g)) else K.IMPL_SIMT

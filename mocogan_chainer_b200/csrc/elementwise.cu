@@ -40,7 +40,7 @@ static int pow2_ge(int x) {
 struct StatsF {  // sum y, sum y^2
   template <int VEC> struct Regs {};
   template <int VEC> __device__ __forceinline__ void prep(int, Regs<VEC>&) const {}
-  static constexpr bool kTwo = false;
+  static constexpr bool kTwo = false, kHasB = true;
   template <int VEC>
   __device__ __forceinline__ void acc(const float (&v)[VEC], const float (&)[VEC], const Regs<VEC>&, float (&a)[VEC],
                                       float (&b)[VEC]) const {
@@ -51,7 +51,7 @@ struct StatsF {  // sum y, sum y^2
 struct SumF {  // sum g
   template <int VEC> struct Regs {};
   template <int VEC> __device__ __forceinline__ void prep(int, Regs<VEC>&) const {}
-  static constexpr bool kTwo = false;
+  static constexpr bool kTwo = false, kHasB = false;
   template <int VEC>
   __device__ __forceinline__ void acc(const float (&v)[VEC], const float (&)[VEC], const Regs<VEC>&, float (&a)[VEC],
                                       float (&)[VEC]) const {
@@ -73,7 +73,7 @@ struct BnBwdF {  // sum g', sum g'*xhat with g' = g * act'(scale*y+shift)
       r.mean[i] = mean[c0 + i]; r.invstd[i] = invstd[c0 + i]; r.scale[i] = scale[c0 + i]; r.shift[i] = shift[c0 + i];
     }
   }
-  static constexpr bool kTwo = true;
+  static constexpr bool kTwo = true, kHasB = true;
   template <int VEC>
   __device__ __forceinline__ void acc(const float (&gv)[VEC], const float (&yv)[VEC], const Regs<VEC>& r, float (&a)[VEC],
                                       float (&b)[VEC]) const {
@@ -87,9 +87,54 @@ struct BnBwdF {  // sum g', sum g'*xhat with g' = g * act'(scale*y+shift)
   }
 };
 
-template <typename T, int VEC, typename F>
+// How a column reduction ends.  The separate finalize kernels (one warp per channel over <= 592 per-block partial rows)
+// were ~50 launches of 5-8 us per step, each a link in a stats -> finalize -> apply dependency chain.  Now every block adds
+// its column sums into one of kRedSlots slot rows with red.add (<= 37 adds per address — a single row serialised ~600) and
+// takes a ticket; the block that draws the last ticket sums the 16 slot rows per channel in double, runs the finaliser
+// (statistics -> mean / invstd / scale / shift / running averages, or plain sums -> outputs) and hands the slot rows and
+// the ticket counter back ZEROED, which is the state every call expects to find them in (mcg.h: the workspace of these
+// entry points must be zero-filled once, at allocation).
+constexpr int kRedSlots = 16;
+struct StatsFinal {
+  double M;
+  const float *gamma, *beta;
+  float eps, decay;
+  float *mean, *invstd, *scale, *shift, *avg_mean, *avg_var;
+  __device__ __forceinline__ void operator()(int c, double s, double q) const {
+    double mu = s / M;
+    double var = q / M - mu * mu;
+    if (var < 0) var = 0;
+    double inv = 1.0 / sqrt(var + (double)eps);
+    mean[c] = (float)mu;
+    invstd[c] = (float)inv;
+    float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    float sc = ga * (float)inv;
+    if (scale) scale[c] = sc;
+    if (shift) shift[c] = be - (float)mu * sc;
+    if (avg_mean) {
+      double adjust = M / (M - 1.0 > 1.0 ? M - 1.0 : 1.0);
+      avg_mean[c] = decay * avg_mean[c] + (1.f - decay) * (float)mu;
+      avg_var[c] = decay * avg_var[c] + (1.f - decay) * (float)(adjust * (var + (double)eps));
+    }
+  }
+};
+struct Sum2Final {
+  float *out_a, *out_b;
+  int accumulate;
+  float *acc_a, *acc_b;
+  __device__ __forceinline__ void operator()(int c, double s, double q) const {
+    // accumulating targets are parameter gradients: the real-clip and fake-clip branches of a pass may finish on two
+    // streams at once, so they are added atomically
+    if (out_a) { if (accumulate) atomicAdd(out_a + c, (float)s); else out_a[c] = (float)s; }
+    if (out_b) { if (accumulate) atomicAdd(out_b + c, (float)q); else out_b[c] = (float)q; }
+    if (acc_a) atomicAdd(acc_a + c, (float)s);
+    if (acc_b) atomicAdd(acc_b + c, (float)q);
+  }
+};
+
+template <typename T, int VEC, typename F, typename FIN>
 __global__ void __launch_bounds__(kRedThreads, F::kTwo ? MCG_RED_MB : 4) colreduce_kernel(F f, const T* p0, const T* p1, long long M, int C,
-                                                               int tpr, float* __restrict__ partial) {
+                                                               int tpr, float* __restrict__ slots, FIN fin) {
   pdl_enter();
   extern __shared__ float red[];  // [rpb][tpr][2*VEC]
   const int CG = C / VEC;
@@ -153,15 +198,45 @@ __global__ void __launch_bounds__(kRedThreads, F::kTwo ? MCG_RED_MB : 4) colredu
 #pragma unroll
       for (int i = 0; i < VEC; ++i) { a[i] += o[i]; b[i] += o[VEC + i]; }
     }
-    float* dst = partial + (size_t)blockIdx.x * 2 * C;
+    float* dst = slots + (size_t)(blockIdx.x % kRedSlots) * 2 * C;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { dst[tx * VEC + i] = a[i]; dst[C + tx * VEC + i] = b[i]; }
+    for (int i = 0; i < VEC; ++i) {
+      atomicAdd(dst + tx * VEC + i, a[i]);
+      if (F::kHasB) atomicAdd(dst + C + tx * VEC + i, b[i]);
+    }
   }
+  // ticket: the last block to arrive sees every block's adds (fence before the ticket, fence after it)
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  int* counter = reinterpret_cast<int*>(slots + (size_t)kRedSlots * 2 * C);
+  if (threadIdx.x == 0) s_last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += kRedThreads) {
+    float sv[kRedSlots], qv[kRedSlots];
+#pragma unroll
+    for (int k = 0; k < kRedSlots; ++k) {
+      sv[k] = __ldcg(slots + (size_t)k * 2 * C + c);
+      qv[k] = F::kHasB ? __ldcg(slots + (size_t)k * 2 * C + C + c) : 0.f;
+    }
+    double sd = 0, qd = 0;
+#pragma unroll
+    for (int k = 0; k < kRedSlots; ++k) { sd += (double)sv[k]; qd += (double)qv[k]; }
+#pragma unroll
+    for (int k = 0; k < kRedSlots; ++k) {
+      slots[(size_t)k * 2 * C + c] = 0.f;
+      if (F::kHasB) slots[(size_t)k * 2 * C + C + c] = 0.f;
+    }
+    fin(c, sd, qd);
+  }
+  if (threadIdx.x == 0) *counter = 0;
 }
 
-template <typename F>
-static int launch_colreduce(F f, const void* p0, const void* p1, long long M, int C, int dtype, void* ws,
-                            size_t ws_bytes, cudaStream_t st, int* nblk_out, const char* name) {
+template <typename F, typename FIN>
+static int launch_colreduce(F f, FIN fin, const void* p0, const void* p1, long long M, int C, int dtype, void* ws,
+                            size_t ws_bytes, cudaStream_t st, const char* name) {
   if (M <= 0 || C <= 0) MCG_FAIL(MCG_ERR_SHAPE, "%s: empty matrix M=%lld C=%d", name, M, C);
   const int VEC = (C % 8 == 0) ? 8 : 1;
   const int CG = C / VEC;
@@ -180,10 +255,10 @@ static int launch_colreduce(F f, const void* p0, const void* p1, long long M, in
     if (per_sm < 0) {
       per_sm = 0;
       cudaError_t e = cudaSuccess;
-      if (dtype == MCG_F32) e = VEC == 8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<float, 8, F>, kRedThreads, smem)
-                                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<float, 1, F>, kRedThreads, smem);
-      else e = VEC == 8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<__nv_bfloat16, 8, F>, kRedThreads, smem)
-                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<__nv_bfloat16, 1, F>, kRedThreads, smem);
+      if (dtype == MCG_F32) e = VEC == 8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<float, 8, F, FIN>, kRedThreads, smem)
+                                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<float, 1, F, FIN>, kRedThreads, smem);
+      else e = VEC == 8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<__nv_bfloat16, 8, F, FIN>, kRedThreads, smem)
+                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colreduce_kernel<__nv_bfloat16, 1, F, FIN>, kRedThreads, smem);
       if (e != cudaSuccess) { per_sm = 0; (void)cudaGetLastError(); }
       slot.store(per_sm + 1, std::memory_order_relaxed);
     }
@@ -191,81 +266,16 @@ static int launch_colreduce(F f, const void* p0, const void* p1, long long M, in
   }
   int nblk = (int)(want < cap ? want : cap);
   if (nblk < 1) nblk = 1;
-  if (ws_bytes < (size_t)nblk * 2 * C * sizeof(float) || !ws)
-    MCG_FAIL(MCG_ERR_WORKSPACE, "%s: workspace %zu < %zu", name, ws_bytes, (size_t)nblk * 2 * C * sizeof(float));
-  float* part = reinterpret_cast<float*>(ws);
-#define LAUNCH(T, V) pdl(colreduce_kernel<T, V, F>, nblk, kRedThreads, smem, st)(f, (const T*)p0, (const T*)p1, M, C, tpr, part)
+  const size_t need = (size_t)kRedSlots * 2 * C * sizeof(float) + 16;
+  if (ws_bytes < need || !ws) MCG_FAIL(MCG_ERR_WORKSPACE, "%s: workspace %zu < %zu", name, ws_bytes, need);
+  float* part = reinterpret_cast<float*>(ws);   // kRedSlots x 2C slot sums + the ticket counter, zero on entry and on exit
+#define LAUNCH(T, V) pdl(colreduce_kernel<T, V, F, FIN>, nblk, kRedThreads, smem, st)(f, (const T*)p0, (const T*)p1, M, C, tpr, part, fin)
   if (dtype == MCG_F32) { if (VEC == 8) LAUNCH(float, 8); else LAUNCH(float, 1); }
   else if (dtype == MCG_BF16) { if (VEC == 8) LAUNCH(__nv_bfloat16, 8); else LAUNCH(__nv_bfloat16, 1); }
   else MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: dtype %d", name, dtype);
 #undef LAUNCH
   MCG_CHECK_LAUNCH(name);
-  *nblk_out = nblk;
   return 0;
-}
-
-// One warp per channel: lanes stride over the per-block partials, then a shuffle tree (fixed order: deterministic).
-// Every lane issues ALL of its (at most 19 x 2) loads before the first add — the partials of one channel are 2*C floats
-// apart, so each load is its own L2 round trip and a dependent chain of them was 6-10 us per finalize (x 46 per step).
-__device__ __forceinline__ void warp_sum_partials(const float* partial, int nblk, int C, int c, double& s, double& q) {
-  const int lane = threadIdx.x & 31;
-  constexpr int kPer = (kRedMaxBlocks + 31) / 32;
-  float sv[kPer], qv[kPer];
-#pragma unroll
-  for (int i = 0; i < kPer; ++i) {
-    const int b = lane + 32 * i;
-    const bool ok = b < nblk;
-    sv[i] = ok ? partial[(size_t)b * 2 * C + c] : 0.f;
-    qv[i] = ok ? partial[(size_t)b * 2 * C + C + c] : 0.f;
-  }
-  s = 0; q = 0;
-#pragma unroll
-  for (int i = 0; i < kPer; ++i) { s += (double)sv[i]; q += (double)qv[i]; }
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
-  }
-}
-__global__ void __launch_bounds__(256) bn_stats_finalize(const float* partial, int nblk, int C, double M,
-                                                         const float* gamma, const float* beta, float eps, float decay,
-                                                         float* mean, float* invstd, float* scale, float* shift,
-                                                         float* avg_mean, float* avg_var) {
-  pdl_enter();
-  int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (c >= C) return;
-  double s, q;
-  warp_sum_partials(partial, nblk, C, c, s, q);
-  if (threadIdx.x & 31) return;
-  double mu = s / M;
-  double var = q / M - mu * mu;
-  if (var < 0) var = 0;
-  double inv = 1.0 / sqrt(var + (double)eps);
-  mean[c] = (float)mu;
-  invstd[c] = (float)inv;
-  float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-  float sc = ga * (float)inv;
-  if (scale) scale[c] = sc;
-  if (shift) shift[c] = be - (float)mu * sc;
-  if (avg_mean) {
-    double adjust = M / (M - 1.0 > 1.0 ? M - 1.0 : 1.0);
-    avg_mean[c] = decay * avg_mean[c] + (1.f - decay) * (float)mu;
-    avg_var[c] = decay * avg_var[c] + (1.f - decay) * (float)(adjust * (var + (double)eps));
-  }
-}
-__global__ void __launch_bounds__(256) sum2_finalize(const float* partial, int nblk, int C, float* out_a, float* out_b,
-                                                     int accumulate, float* acc_a = nullptr, float* acc_b = nullptr) {
-  pdl_enter();
-  int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (c >= C) return;
-  double s, q;
-  warp_sum_partials(partial, nblk, C, c, s, q);
-  if (threadIdx.x & 31) return;
-  // accumulating targets are parameter gradients: the real-clip and fake-clip branches of a pass may finish on two
-  // streams at once, so they are added atomically
-  if (out_a) { if (accumulate) atomicAdd(out_a + c, (float)s); else out_a[c] = (float)s; }
-  if (out_b) { if (accumulate) atomicAdd(out_b + c, (float)q); else out_b[c] = (float)q; }
-  if (acc_a) atomicAdd(acc_a + c, (float)s);
-  if (acc_b) atomicAdd(acc_b + c, (float)q);
 }
 
 // =====================================================================================================
@@ -580,6 +590,17 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     if (pb) pb[i] = __float2bfloat16_rn(pi);
   }
 }
+// dst[row][0..Cp) = src[row][0..C) followed by zeros: the generator's 60-channel latent padded to the 64 the tcgen05 path wants
+template <typename T>
+__global__ void __launch_bounds__(256) pad_channels_kernel(const T* __restrict__ src, T* __restrict__ dst, long long rows, int C, int Cp) {
+  pdl_enter();
+  const long long total = rows * Cp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / Cp;
+    const int c = (int)(i - r * Cp);
+    dst[i] = c < C ? src[r * C + c] : T(0.f);
+  }
+}
 __global__ void cast_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
   pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -647,35 +668,22 @@ long long mcg_launch_count(void) { return g_launches.load(); }
 
 size_t mcg_colreduce_workspace_bytes(long long M, int C) {
   (void)M;
-  return (size_t)kRedMaxBlocks * 2 * (size_t)(C > 0 ? C : 1) * sizeof(float);
+  return (size_t)kRedSlots * 2 * (size_t)(C > 0 ? C : 1) * sizeof(float) + 256;
 }
 
 int mcg_bn_stats(const void* y, long long M, int C, int dtype, const float* gamma, const float* beta, float eps,
                  float decay, float* mean, float* invstd, float* scale, float* shift, float* avg_mean, float* avg_var,
                  void* workspace, size_t workspace_bytes, void* stream) {
   if (!y || !mean || !invstd) MCG_FAIL(MCG_ERR_SHAPE, "mcg_bn_stats: null pointer");
-  int nblk = 0;
-  int rc = launch_colreduce(StatsF{}, y, nullptr, M, C, dtype, workspace, workspace_bytes, as_stream(stream), &nblk,
-                            "mcg_bn_stats");
-  if (rc) return rc;
-  pdl(bn_stats_finalize, (C + 7) / 8, 256, 0, as_stream(stream))((const float*)workspace, nblk, C, (double)M, gamma,
-                                                                    beta, eps, decay, mean, invstd, scale, shift,
-                                                                    avg_mean, avg_var);
-  MCG_CHECK_LAUNCH("mcg_bn_stats(finalize)");
-  return 0;
+  return launch_colreduce(StatsF{}, StatsFinal{(double)M, gamma, beta, eps, decay, mean, invstd, scale, shift, avg_mean, avg_var},
+                          y, nullptr, M, C, dtype, workspace, workspace_bytes, as_stream(stream), "mcg_bn_stats");
 }
 
 int mcg_colsum(const void* g, long long M, int C, int dtype, float* out, int accumulate, void* workspace,
                size_t workspace_bytes, void* stream) {
   if (!g || !out) MCG_FAIL(MCG_ERR_SHAPE, "mcg_colsum: null pointer");
-  int nblk = 0;
-  int rc = launch_colreduce(SumF{}, g, nullptr, M, C, dtype, workspace, workspace_bytes, as_stream(stream), &nblk,
-                            "mcg_colsum");
-  if (rc) return rc;
-  pdl(sum2_finalize, (C + 7) / 8, 256, 0, as_stream(stream))((const float*)workspace, nblk, C, out, nullptr,
-                                                                accumulate, nullptr, nullptr);
-  MCG_CHECK_LAUNCH("mcg_colsum(finalize)");
-  return 0;
+  return launch_colreduce(SumF{}, Sum2Final{out, nullptr, accumulate, nullptr, nullptr}, g, nullptr, M, C, dtype, workspace,
+                          workspace_bytes, as_stream(stream), "mcg_colsum");
 }
 
 int mcg_act_bn_bwd_reduce(const void* g, const void* y, long long M, int C, int dtype, const float* mean,
@@ -684,22 +692,16 @@ int mcg_act_bn_bwd_reduce(const void* g, const void* y, long long M, int C, int 
                           size_t workspace_bytes, void* stream) {
   if (!g || !y || !mean || !invstd || !scale || !shift || !dgamma || !dbeta)
     MCG_FAIL(MCG_ERR_SHAPE, "mcg_act_bn_bwd_reduce: null pointer");
-  int nblk = 0;
-  int rc;
-#define MCG_RED(A) rc = launch_colreduce(BnBwdF<A>{mean, invstd, scale, shift, act, slope}, g, y, M, C, dtype, workspace, \
-                                         workspace_bytes, as_stream(stream), &nblk, "mcg_act_bn_bwd_reduce")
+  // first sum = sum g' -> dbeta ; second = sum g' xhat -> dgamma; acc_* are the parameter gradients, which accumulate
+  // across the real and fake calls of one pass as in Chainer.
+  const Sum2Final fin{dbeta, dgamma, 0, acc_dbeta, acc_dgamma};
+#define MCG_RED(A) return launch_colreduce(BnBwdF<A>{mean, invstd, scale, shift, act, slope}, fin, g, y, M, C, dtype, workspace, \
+                                           workspace_bytes, as_stream(stream), "mcg_act_bn_bwd_reduce")
   if (C % 8) MCG_RED(-1);
   else if (act == MCG_ACT_RELU) MCG_RED(MCG_ACT_RELU);
   else if (act == MCG_ACT_LRELU) MCG_RED(MCG_ACT_LRELU);
   else MCG_RED(-1);
 #undef MCG_RED
-  if (rc) return rc;
-  // partial[.,0,:] = sum g' -> dbeta ; partial[.,1,:] = sum g' xhat -> dgamma; acc_* are the parameter
-  // gradients, which accumulate across the real and fake calls of one pass as in Chainer.
-  pdl(sum2_finalize, (C + 7) / 8, 256, 0, as_stream(stream))((const float*)workspace, nblk, C, dbeta, dgamma, 0,
-                                                                acc_dbeta, acc_dgamma);
-  MCG_CHECK_LAUNCH("mcg_act_bn_bwd_reduce(finalize)");
-  return 0;
 }
 
 int mcg_affine_act_noise(const void* y, long long M, int C, long long P, int dtype, const float* scale,
@@ -871,6 +873,23 @@ int mcg_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, lo
   pdl(adam_kernel, grid_for(n), 256, 0, as_stream(stream))(p, g, m, v, (__nv_bfloat16*)p_bf16, n, alpha, beta1, beta2,
                                                           eps, wd, grad_scale, t_ptr);
   MCG_CHECK_LAUNCH("mcg_adam_step");
+  return 0;
+}
+
+int mcg_fill_zero(void* p, size_t bytes, void* stream) {
+  if (!p && bytes) MCG_FAIL(MCG_ERR_SHAPE, "mcg_fill_zero: null pointer");
+  cudaError_t e = cudaMemsetAsync(p, 0, bytes, as_stream(stream));     // a memset node when captured: no kernel, no SM
+  if (e != cudaSuccess) MCG_FAIL((int)e, "mcg_fill_zero: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int mcg_pad_channels(const void* src, void* dst, long long rows, int C, int Cp, int dtype, void* stream) {
+  if (!src || !dst || rows <= 0 || C <= 0 || Cp < C) MCG_FAIL(MCG_ERR_SHAPE, "mcg_pad_channels: bad arguments");
+  const int grid = grid_for(rows * Cp);
+  if (dtype == MCG_BF16) pdl(pad_channels_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream))((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, rows, C, Cp);
+  else if (dtype == MCG_F32) pdl(pad_channels_kernel<float>, grid, 256, 0, as_stream(stream))((const float*)src, (float*)dst, rows, C, Cp);
+  else MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_pad_channels: dtype %d", dtype);
+  MCG_CHECK_LAUNCH("mcg_pad_channels");
   return 0;
 }
 

@@ -65,6 +65,9 @@ struct TcParams {
   // 23 % (dc2) to 43 % (dc4) of their K steps that way.  Taps are kt-major, so the taps worth issuing for a segment are
   // one contiguous run: tap-group index i (skip_per_kt taps each) reads frame t*a_mul_t + a_add_t + skip_dt0 + i*skip_dts.
   int skip_t, skip_per_kt[8], skip_nkt, skip_dt0, skip_dts, skip_aT;   // skip_per_kt: per stride class
+  int str_rounds, str_rem_per; long long str_rem0;   // strided: full rounds of groups, then total - str_rem0 left-over units dealt str_rem_per per CTA
+  int strided;  // > 0: CTA c takes the unit groups c, c + grid, c + 2*grid, ... of `strided` units each (boxes cost
+                // different numbers of K steps once taps are skipped; contiguous ranges would be frame-coherent and uneven)
   int box_tn;   // 1: boxes are numbered (w, h, n, t) — frames slowest — so the MT boxes of a step share their frame and skip alike
   int debug_skip_epi;
   int out_f32, ocols;                                        // ocols = channels of one output pixel row
@@ -168,13 +171,27 @@ __device__ __forceinline__ int tc_sched_chunk(int total, int handed_out, int mt)
 struct TcRanges {
   uint32_t full_a, empty_a;
   const TcSchedSmem* sm;
-  int slot;
+  int slot, grp;
   uint32_t ph;
   bool dyn, done;
   __device__ __forceinline__ TcRanges(const TcParams& P, const TcSchedSmem* sm_, uint32_t full, uint32_t empty)
-      : full_a(full), empty_a(empty), sm(sm_), slot(0), ph(0), dyn(P.dyn != 0), done(false) {}
+      : full_a(full), empty_a(empty), sm(sm_), slot(0), grp(0), ph(0), dyn(P.dyn != 0), done(false) {}
   __device__ __forceinline__ bool next(const TcParams& P, long long& u, long long& u_end, int* err) {
     if (!dyn) {
+      if (P.strided) {
+        if (grp < P.str_rounds) {
+          u = ((long long)blockIdx.x + (long long)grp * gridDim.x) * P.strided;
+          u_end = u + P.strided;
+        } else if (grp == P.str_rounds) {   // what the full rounds left over, cut evenly (unit, not group, granularity)
+          u = P.str_rem0 + (long long)blockIdx.x * P.str_rem_per;
+          u_end = u + P.str_rem_per;
+          if (u_end > P.total_units) u_end = P.total_units;
+        } else {
+          return false;
+        }
+        ++grp;
+        return u < u_end;
+      }
       if (done) return false;
       done = true;
       u = (long long)blockIdx.x * P.units_per_cta;
@@ -414,6 +431,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
           nxt_c = tc_sched_chunk(total, cur_u0 + cur_c, MT);
           nxt_u0 = atomicAdd(&g_tc_sched_ctr[P.sched_slot], nxt_c);   // consumed when this range's loads are issued
           iter.set(cur_u0, (long long)cur_u0 + n);
+        } else if (P.strided) {
+          long long gu, ge;                           // cur_c counts groups here (same sequence as TcRanges::next)
+          if (cur_c < P.str_rounds) {
+            gu = ((long long)blockIdx.x + (long long)cur_c * gridDim.x) * P.strided;
+            ge = gu + P.strided;
+          } else if (cur_c == P.str_rounds) {
+            gu = P.str_rem0 + (long long)blockIdx.x * P.str_rem_per;
+            ge = gu + P.str_rem_per < P.total_units ? gu + P.str_rem_per : P.total_units;
+          } else {
+            break;
+          }
+          ++cur_c;
+          if (gu >= ge) break;
+          iter.set(gu, ge);
         } else {
           if (static_done) break;
           static_done = true;
@@ -889,6 +920,18 @@ static void tc_set_schedule(TcParams& P, int mode, int grid, int mt) {
   }
   P.dyn = 0;
   P.sched_slot = 0;
+  // Strided groups make the skipped taps balance across CTAs, but CTAs then walk neighbouring boxes of one class in
+  // lock-step; measured (B200, Dv layers): a win for the 64-column data gradients (weights are 11 % of a step's bytes), a
+  // loss for the 128/256-column ones (33-50 %), which keep contiguous ranges and skip what their mixed-frame steps allow.
+  const int fs = tc_env_int("MCG_TC_STRIDED");     // 1 / -1 force on / off
+  const bool strided = fs > 0 || (fs == 0 && P.box_tn);
+  P.strided = (mode != kWgrad && P.skip_t && strided) ? mt : 0;
+  if (P.strided) {
+    P.str_rounds = (int)((P.total_units / mt) / grid);
+    P.str_rem0 = (long long)P.str_rounds * grid * mt;
+    P.str_rem_per = (int)((P.total_units - P.str_rem0 + grid - 1) / grid);
+    return;
+  }
   if (dyn && mode != kWgrad && P.total_units < (1LL << 30) && P.total_units >= 4LL * grid * mt) {
     P.dyn = 1;
     P.sched_slot = (int)(g_tc_sched_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
@@ -1033,9 +1076,9 @@ static bool tr_wanted(const TrPlan& tr, double plain_cost) {
 // the TMA ring keeps loading the next tile under the epilogue).  Per (kt, chunk) and 256 pixels the SM pulls
 // 2 x 9 x 16 KB of dy + 16 x 8 KB of weights = 416 KB instead of 576 KB, and issues 40 wide MMAs instead of 64 narrow
 // ones.  Temporal taps whose dy frame lies outside the clip are skipped like in the plain kernel.
-// Work split: every CTA owns q = blocks / grid consecutive 128-pixel blocks (walked in pairs); the blocks % grid
-// left-over blocks are cut into their four classes and dealt round-robin as single-class units (4 boxes, N = 64), so no
-// CTA carries a whole extra block.
+// Work split: boxes are numbered (w, h, n, t) — frames slowest — and CTA c takes the block pairs c, c + grid, c + 2*grid, ...:
+// the two blocks of a pair share their frame (so they skip the same temporal taps), every CTA samples all frames (so the
+// skipped taps balance), and the pairs left over after the last full round lie in the last frame, the cheapest one.
 // =============================================================================================================
 struct Tc4Stage {
   int8_t dh, dw;            // dy box offset
@@ -1050,31 +1093,59 @@ struct Tc4Params {
   int EN, full_w, full_h, full_t;
   long long os_w, os_h, os_t, os_n;
   int chunks, kT, kHW, pT, aT, Cin;
-  int nblocks, q, rem_units, rem_block0;
+  int nblocks, rounds, rem0, rem_per;
   int out_f32;
-  int nst[5];               // stages of schedule 0 (all classes) and 1 + c (class c only)
+  int nst;                  // stages per (kt, chunk): the 9 offsets, widest first
   uint8_t cls_at_slot[4], slot_of_cls[4];
-  Tc4Stage st[5][9];
+  Tc4Stage st[9];
 };
-constexpr int kT4Small = 2 * A_BYTES + 2 * 8192, kT4Big = 2 * A_BYTES + 4 * 8192, kT4SmallSlots = 3;
-constexpr int kT4Smem = kT4Big + kT4SmallSlots * kT4Small + 1024;
+// The stage table of the one geometry this kernel takes (k = 4, s = 2, p = 1), as compile-time constants: the producer
+// and MMA loops are single threads whose issue rate bounds the kernel, and a table read from the parameter bank with a
+// run-time index (LDC c[0x0][R + ...]) stalled the MMA thread on its long scoreboard for two thirds of its samples
+// (profiles/r02_ncu_dv_dc2.txt).  The host still derives the table from the tap geometry and refuses to launch unless it
+// equals this one.  Classes c = ph*2 + pw sit in TMEM slots (0,0) (0,1) (1,1) (1,0) = c 0, 1, 3, 2.
+struct Tc4StageC { int dh, dw, nslab, nmma, khkw[4], col[2], n[2], slab[2]; };
+__device__ constexpr Tc4StageC kTc4[9] = {
+    {0, 0, 4, 1, {5, 6, 10, 9}, {0, 0}, {4, 0}, {0, 0}},      // centre: all four classes, one N = 256 MMA
+    {-1, 0, 2, 1, {13, 14, 0, 0}, {0, 0}, {2, 0}, {0, 0}},    // ph = 0 row above: classes (0,0) (0,1)
+    {0, -1, 2, 2, {7, 11, 0, 0}, {0, 3}, {1, 1}, {0, 1}},     // pw = 0 column left: classes (0,0) and (1,0), not adjacent
+    {0, 1, 2, 1, {4, 8, 0, 0}, {1, 0}, {2, 0}, {0, 0}},       // pw = 1 column right: classes (0,1) (1,1)
+    {1, 0, 2, 1, {2, 1, 0, 0}, {2, 0}, {2, 0}, {0, 0}},       // ph = 1 row below: classes (1,1) (1,0)
+    {-1, -1, 1, 1, {15, 0, 0, 0}, {0, 0}, {1, 0}, {0, 0}},    // corners: one class each
+    {-1, 1, 1, 1, {12, 0, 0, 0}, {1, 0}, {1, 0}, {0, 0}},
+    {1, -1, 1, 1, {3, 0, 0, 0}, {3, 0}, {1, 0}, {0, 0}},
+    {1, 1, 1, 1, {0, 0, 0, 0}, {2, 0}, {1, 0}, {0, 0}},
+};
+// Shared-memory ring in 8 KB granules.  A stage's pieces (a 16 KB dy tile per live block, one run of 1 / 2 / 4 adjacent
+// weight slabs per MMA) are placed one after another; a piece that would cross the end of the ring starts over at 0.
+// Stage sizes differ (40 - 64 KB), so fixed slots would leave a third of the ring idle — and what bounds these kernels
+// is bytes in flight per SM (Little's law against the L2 round trip), not the number of stages.
+constexpr int kT4Gran = 8192, kT4RingGr = 27, kT4Bars = 8;
+constexpr int kT4Smem = kT4RingGr * kT4Gran + 1024;
+__device__ __forceinline__ int tc4_take(int& head, int n, int& foot) {
+  if (head + n > kT4RingGr) { foot += kT4RingGr - head; head = 0; }
+  const int a = head;
+  head += n;
+  foot += n;
+  return a;
+}
 
-struct Tc4Seg { int box0, nlive, sched, kt_lo, kt_n; };
+struct Tc4Seg { int box0, nlive, kt_lo, kt_n; };
 struct Tc4Iter {
-  int b, b_end, u, phase;
-  __device__ __forceinline__ explicit Tc4Iter(const Tc4Params& P) {
-    b = (int)blockIdx.x * P.q; b_end = b + P.q; u = (int)blockIdx.x; phase = 0;
-  }
+  int k;
+  __device__ __forceinline__ explicit Tc4Iter(const Tc4Params&) : k(0) {}
   __device__ __forceinline__ bool next(const Tc4Params& P, Tc4Seg& s) {
-    if (b < b_end) {
-      s.box0 = b; s.nlive = b_end - b >= 2 ? 2 : 1; s.sched = 0;
-      b += s.nlive;
-    } else if (u < P.rem_units) {
-      s.box0 = P.rem_block0 + (u >> 2); s.nlive = 1; s.sched = 1 + (u & 3);
-      u += (int)gridDim.x;
+    if (k < P.rounds) {
+      s.box0 = 2 * ((int)blockIdx.x + k * (int)gridDim.x);
+      s.nlive = 2;
+    } else if (k == P.rounds) {     // the blocks the full rounds left over: rem_per (1 or 2) per CTA
+      s.box0 = P.rem0 + (int)blockIdx.x * P.rem_per;
+      s.nlive = P.nblocks - s.box0 < P.rem_per ? P.nblocks - s.box0 : P.rem_per;
+      if (s.nlive <= 0) return false;
     } else {
       return false;
     }
+    ++k;
     // temporal taps worth issuing: dy frame = t + pT - kt must meet [0, aT) for some frame t of the step's boxes
     // (boxes are numbered (w, h, n, t): the two blocks of a pair share their frame except once per frame change)
     const int per_t = P.nbw * P.nbh * P.nbb;
@@ -1102,12 +1173,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dgrad4_kernel(const __grid_c
   pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[1 + kT4SmallSlots], empty_bar[1 + kT4SmallSlots], tfull_bar, tempty_bar;
+  __shared__ uint64_t full_bar[kT4Bars], empty_bar[kT4Bars], tfull_bar, tempty_bar;
+  __shared__ int ring_fp[kT4Bars];      // granules (waste included) each in-flight stage holds; producer thread only
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* err = &g_tc_error;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 1 + kT4SmallSlots; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < kT4Bars; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&tfull_bar, 1);
     mbar_init(&tempty_bar, kEpiThreads);
     fence_barrier_init();
@@ -1121,7 +1193,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dgrad4_kernel(const __grid_c
   const uint32_t tmem = tmem_slot;
   pdl_wait();
 
-  // ring: slot 0 = the 4-slab slot (the centre offset's stage), slots 1..3 = 2-slab slots; A first, then the slabs
   const uint32_t smem_a = smem_u32(smem);
   const uint32_t full_a = smem_u32(&full_bar[0]), empty_a = smem_u32(&empty_bar[0]);
   const uint32_t tfull_a = smem_u32(&tfull_bar), tempty_a = smem_u32(&tempty_bar);
@@ -1131,30 +1202,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dgrad4_kernel(const __grid_c
       const uint64_t map_a = reinterpret_cast<uint64_t>(&mapA), map_b = reinterpret_cast<uint64_t>(&mapB);
       Tc4Iter iter(P);
       Tc4Seg sg;
-      uint32_t ph_big = 1, ph_small = 1;
-      int si = 0;
+      int head = 0, freeg = kT4RingGr, istage = 0, tail = 0;
       bool alive = true;
       while (alive && iter.next(P, sg)) {
         TcBox bx[2];
         bx[0] = tc4_decode_box(P, sg.box0);
         bx[1] = tc4_decode_box(P, sg.box0 + (sg.nlive > 1 ? 1 : 0));
-        const int nst = P.nst[sg.sched];
         for (int kt = sg.kt_lo; alive && kt < sg.kt_lo + sg.kt_n; ++kt) {
           const int dt = P.pT - kt, kbase = kt * P.kHW;
           for (int c = 0; alive && c < P.chunks; ++c) {
-            for (int s = 0; s < nst; ++s) {
-              const Tc4Stage& st = P.st[sg.sched][s];
-              uint32_t slot, ph;
-              if (st.big) { slot = 0; ph = ph_big; ph_big ^= 1; }
-              else { slot = 1 + si; ph = ph_small; if (++si == kT4SmallSlots) { si = 0; ph_small ^= 1; } }
-              const uint32_t base = smem_a + (slot ? kT4Big + (slot - 1) * kT4Small : 0), fb = full_a + slot * 8;
-              if (!mbar_wait_a(empty_a + slot * 8, ph, err)) { alive = false; break; }
-              mbar_expect_tx_a(fb, sg.nlive * A_BYTES + st.nslab * 8192);
-              tma_load_5d_a(base, map_a, fb, c * 64, bx[0].w0 + st.dw, bx[0].h0 + st.dh, bx[0].t0 + dt, bx[0].n0);
+#pragma unroll
+            for (int s = 0; s < 9; ++s) {
+              constexpr const Tc4StageC* T = kTc4;
+              int h = head, foot = 0;
+              const int a0 = tc4_take(h, 2, foot), a1 = sg.nlive > 1 ? tc4_take(h, 2, foot) : 0;
+              const int b0 = tc4_take(h, T[s].n[0], foot), b1 = T[s].nmma > 1 ? tc4_take(h, T[s].n[1], foot) : 0;
+              // room: stages retire in order; wait for as many of the oldest as this one's footprint (or a barrier pair) needs
+              while (freeg < foot || istage - tail >= kT4Bars) {
+                if (!mbar_wait_a(empty_a + (tail % kT4Bars) * 8, (tail / kT4Bars) & 1, err)) { alive = false; break; }
+                freeg += ring_fp[tail % kT4Bars];
+                ++tail;
+              }
+              if (!alive) break;
+              head = h; freeg -= foot; ring_fp[istage % kT4Bars] = foot;
+              const uint32_t fb = full_a + (istage % kT4Bars) * 8;
+              ++istage;
+              mbar_expect_tx_a(fb, sg.nlive * A_BYTES + T[s].nslab * 8192);
+              tma_load_5d_a(smem_a + a0 * kT4Gran, map_a, fb, c * 64, bx[0].w0 + T[s].dw, bx[0].h0 + T[s].dh, bx[0].t0 + dt, bx[0].n0);
               if (sg.nlive > 1)
-                tma_load_5d_a(base + A_BYTES, map_a, fb, c * 64, bx[1].w0 + st.dw, bx[1].h0 + st.dh, bx[1].t0 + dt, bx[1].n0);
-              for (int sl = 0; sl < st.nslab; ++sl)
-                tma_load_2d_a(base + 2 * A_BYTES + sl * 8192, map_b, fb, (kbase + st.khkw[sl]) * P.Cin, c * 64);
+                tma_load_5d_a(smem_a + a1 * kT4Gran, map_a, fb, c * 64, bx[1].w0 + T[s].dw, bx[1].h0 + T[s].dh, bx[1].t0 + dt, bx[1].n0);
+#pragma unroll
+              for (int sl = 0; sl < T[s].n[0]; ++sl)
+                tma_load_2d_a(smem_a + (b0 + sl) * kT4Gran, map_b, fb, (kbase + T[s].khkw[sl]) * 64, c * 64);
+              if (T[s].nmma > 1) {
+#pragma unroll
+                for (int sl = 0; sl < T[s].n[1]; ++sl)
+                  tma_load_2d_a(smem_a + (b1 + sl) * kT4Gran, map_b, fb, (kbase + T[s].khkw[T[s].slab[1] + sl]) * 64, c * 64);
+              }
             }
           }
         }
@@ -1166,38 +1250,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dgrad4_kernel(const __grid_c
       const uint32_t id64 = make_idesc_bf16(128, 64, 0, 1), id128 = make_idesc_bf16(128, 128, 0, 1), id256 = make_idesc_bf16(128, 256, 0, 1);
       Tc4Iter iter(P);
       Tc4Seg sg;
-      uint32_t ph_big = 0, ph_small = 0, nseg = 0;
-      int si = 0;
+      uint32_t nseg = 0;
+      int head = 0, istage = 0;
       bool alive = true;
       while (alive && iter.next(P, sg)) {
         if (sg.kt_n == 0) continue;
         if (!mbar_wait_a(tempty_a, (nseg & 1) ^ 1, err)) break;
         tc_fence_after();
-        const int nst = P.nst[sg.sched];
         const int steps = sg.kt_n * P.chunks;
         bool first = true;
         for (int g = 0; alive && g < steps; ++g) {
-          for (int s = 0; s < nst; ++s) {
-            const Tc4Stage& st = P.st[sg.sched][s];
-            uint32_t slot, ph;
-            if (st.big) { slot = 0; ph = ph_big; ph_big ^= 1; }
-            else { slot = 1 + si; ph = ph_small; if (++si == kT4SmallSlots) { si = 0; ph_small ^= 1; } }
-            const uint32_t base = smem_a + (slot ? kT4Big + (slot - 1) * kT4Small : 0);
-            if (!mbar_wait_a(full_a + slot * 8, ph, err)) { alive = false; break; }
+#pragma unroll
+          for (int s = 0; s < 9; ++s) {
+            constexpr const Tc4StageC* T = kTc4;
+            int foot = 0;        // the same placement the producer computed
+            const int a0 = tc4_take(head, 2, foot), a1 = sg.nlive > 1 ? tc4_take(head, 2, foot) : 0;
+            const int b0 = tc4_take(head, T[s].n[0], foot), b1 = T[s].nmma > 1 ? tc4_take(head, T[s].n[1], foot) : 0;
+            const int bar = istage % kT4Bars;
+            if (!mbar_wait_a(full_a + bar * 8, (istage / kT4Bars) & 1, err)) { alive = false; break; }
+            ++istage;
             tc_fence_after();
-            const uint32_t a_lo = smem_desc_lo(base, 16), b_lo = smem_desc_lo(base + 2 * A_BYTES, 8192);
             for (int m = 0; m < sg.nlive; ++m) {
-              for (int j = 0; j < st.nmma; ++j) {
-                const uint32_t d = tmem + m * 256 + st.mma_col[j] * 64;
-                const uint32_t id = st.mma_n[j] == 4 ? id256 : (st.mma_n[j] == 2 ? id128 : id64);
-                const uint32_t bj = b_lo + st.mma_slab[j] * (8192 >> 4);
+              const uint32_t a_lo = smem_desc_lo(smem_a + (m ? a1 : a0) * kT4Gran, 16);
+#pragma unroll
+              for (int j = 0; j < T[s].nmma; ++j) {
+                const uint32_t d = tmem + m * 256 + T[s].col[j] * 64;
+                const uint32_t id = T[s].n[j] == 4 ? id256 : (T[s].n[j] == 2 ? id128 : id64);
+                const uint32_t bj = smem_desc_lo(smem_a + (j ? b1 : b0) * kT4Gran, 8192);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16_lh(d, a_lo + m * (A_BYTES >> 4) + k * 2, desc_hi, bj + k * (2048 >> 4), desc_hi, id,
-                               (first && k == 0) ? 0u : 1u);
+                  umma_bf16_lh(d, a_lo + k * 2, desc_hi, bj + k * (2048 >> 4), desc_hi, id, (first && k == 0) ? 0u : 1u);
               }
             }
-            umma_commit_a(empty_a + slot * 8);
+            umma_commit_a(empty_a + bar * 8);
             first = false;
           }
         }
@@ -1227,14 +1312,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dgrad4_kernel(const __grid_c
         tc_fence_after();
       }
       const uint32_t acc = tmem + (uint32_t(q * 32) << 16);
-      const int s_lo = sg.sched ? P.slot_of_cls[sg.sched - 1] : 0, s_hi = sg.sched ? s_lo + 1 : 4;
+      const int s_lo = 0, s_hi = 4;
 #pragma unroll 1
       for (int m = 0; m < sg.nlive; ++m) {
         const TcBox bx = tc4_decode_box(P, sg.box0 + m);
         const int on = bx.n0 + ib, ot = bx.t0 + itt;
 #pragma unroll 1
         for (int sl = s_lo; sl < s_hi; ++sl) {
-          const int cls = P.cls_at_slot[sl];
+          const int cls = sl ^ (sl >> 1);      // TMEM slot -> class: 0, 1, 3, 2 (kTc4's column order)
           const int ow = (bx.w0 + iw) * 2 + (cls & 1), oh = (bx.h0 + ih) * 2 + (cls >> 1);
           const bool valid = ow < P.full_w && oh < P.full_h && ot < P.full_t && on < P.EN;
           uint32_t v[32];
@@ -1305,9 +1390,9 @@ static int tc_dgrad4(const mcg_conv_geom* g, const void* dy, const void* w, void
   P.chunks = g->Cout / 64; P.kT = g->kT; P.kHW = g->kH * g->kW; P.pT = g->pT; P.aT = g->To; P.Cin = g->Cin;
   P.out_f32 = (out_dtype == MCG_F32);
   const int grid = sms;
-  P.q = P.nblocks / grid;
-  P.rem_block0 = P.q * grid;
-  P.rem_units = 4 * (P.nblocks - P.rem_block0);
+  P.rounds = (P.nblocks / 2) / grid;
+  P.rem0 = P.rounds * grid * 2;
+  P.rem_per = (P.nblocks - P.rem0 + grid - 1) / grid;     // 0, 1 or 2
   // classes c = ph*2 + pw in the cyclic TMEM order (0,0) (0,1) (1,1) (1,0)
   const uint8_t order[4] = {0, 1, 3, 2};
   for (int s = 0; s < 4; ++s) { P.cls_at_slot[s] = order[s]; P.slot_of_cls[order[s]] = (uint8_t)s; }
@@ -1326,7 +1411,8 @@ static int tc_dgrad4(const mcg_conv_geom* g, const void* dy, const void* w, void
       }
     }
   }
-  auto build = [&](int sched, int only_cls) -> int {
+  auto build = [&]() -> int {
+    const int only_cls = -1;
     int n = 0;
     for (int pass = 4; pass >= 1; --pass)            // widest stages first: the first stage of a tile must cover every column
       for (int a = 0; a < 3; ++a)
@@ -1336,7 +1422,7 @@ static int tc_dgrad4(const mcg_conv_geom* g, const void* dy, const void* w, void
             if (only_cls < 0 || x.cls == only_cls) u.push_back(x);
           if ((int)u.size() != pass) continue;
           if (only_cls >= 0 && pass != 1) continue;
-          Tc4Stage& s = P.st[sched][n++];
+          Tc4Stage& s = P.st[n++];
           memset(&s, 0, sizeof(s));
           s.dh = (int8_t)(a - 1); s.dw = (int8_t)(b - 1);
           // slabs in TMEM slot order
@@ -1359,12 +1445,24 @@ static int tc_dgrad4(const mcg_conv_geom* g, const void* dy, const void* w, void
         }
     return n;
   };
-  P.nst[0] = build(0, -1);
-  for (int c = 0; c < 4; ++c) P.nst[1 + c] = build(1 + c, c);
-  if (P.nst[0] != 9 || P.st[0][0].nslab != 4 || P.st[0][0].nmma != 1)
-    MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: unexpected stage table (%d stages)", who, P.nst[0]);
-  for (int c = 0; c < 4; ++c)
-    if (P.nst[1 + c] != 4) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: unexpected class stage table", who);
+  P.nst = build();
+  if (P.nst != 9) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: unexpected stage table (%d stages)", who, P.nst);
+  {
+    static const Tc4StageC kHost[9] = {
+        {0, 0, 4, 1, {5, 6, 10, 9}, {0, 0}, {4, 0}, {0, 0}},   {-1, 0, 2, 1, {13, 14, 0, 0}, {0, 0}, {2, 0}, {0, 0}},
+        {0, -1, 2, 2, {7, 11, 0, 0}, {0, 3}, {1, 1}, {0, 1}},  {0, 1, 2, 1, {4, 8, 0, 0}, {1, 0}, {2, 0}, {0, 0}},
+        {1, 0, 2, 1, {2, 1, 0, 0}, {2, 0}, {2, 0}, {0, 0}},    {-1, -1, 1, 1, {15, 0, 0, 0}, {0, 0}, {1, 0}, {0, 0}},
+        {-1, 1, 1, 1, {12, 0, 0, 0}, {1, 0}, {1, 0}, {0, 0}},  {1, -1, 1, 1, {3, 0, 0, 0}, {3, 0}, {1, 0}, {0, 0}},
+        {1, 1, 1, 1, {0, 0, 0, 0}, {2, 0}, {1, 0}, {0, 0}}};
+    for (int i = 0; i < 9; ++i) {      // the kernel's compile-time table must be what the tap geometry gives
+      const Tc4Stage& a = P.st[i];
+      const Tc4StageC& b = kHost[i];
+      bool same = a.dh == b.dh && a.dw == b.dw && a.nslab == b.nslab && a.nmma == b.nmma;
+      for (int k = 0; same && k < a.nslab; ++k) same = a.khkw[k] == b.khkw[k];
+      for (int k = 0; same && k < a.nmma; ++k) same = a.mma_col[k] == b.col[k] && a.mma_n[k] == b.n[k] && a.mma_slab[k] == b.slab[k];
+      if (!same) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: stage %d of the derived table differs from the kernel's", who, i);
+    }
+  }
   CUtensorMap ma, mb;
   int rc;
   if ((rc = act_map(&ma, dy, g->Cout, g->Wo, g->Ho, g->To, g->N, bx.w, bx.h, bx.t, bx.b, 1, 1, 1))) return rc;
@@ -1463,7 +1561,7 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
     if ((rc = act_map(&ma, a, g->Cin, g->Wi, g->Hi, g->Ti, g->N, bx.w, bx.h, bx.t, bx.b, g->sW, g->sH, g->sT))) return rc;
     if (g->kT > 1 && g->pT > 0 && !tc_env_int("MCG_TC_NOSKIP")) {   // temporal zero padding: edge boxes skip the taps that read only padding
       P.skip_t = 1; P.skip_per_kt[0] = g->kH * g->kW; P.skip_nkt = g->kT; P.skip_dt0 = 0; P.skip_dts = 1; P.skip_aT = g->Ti;
-      P.box_tn = 1;
+      P.box_tn = tc_env_int("MCG_TC_STRIDED") > 0 || (tc_env_int("MCG_TC_STRIDED") == 0 && cfg.bn == 64);
     }
     P.ntn = g->Cout / cfg.bn;
     P.ntiles = P.ntn;
@@ -1556,7 +1654,7 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
     if (g->kT > 1 && ct == 1 && !tc_env_int("MCG_TC_NOSKIP")) {
       // input frame t reads dy frame t + pT - kt: near both ends of the clip most temporal taps fall outside dy (To < Ti)
       P.skip_t = 1; P.skip_nkt = g->kT; P.skip_dt0 = g->pT; P.skip_dts = -1; P.skip_aT = g->To;
-      P.box_tn = 1;
+      P.box_tn = tc_env_int("MCG_TC_STRIDED") > 0 || (tc_env_int("MCG_TC_STRIDED") == 0 && cfg.bn == 64);
       for (int c = 0; c < ncls; ++c) P.skip_per_kt[c] = P.tap_count[c] / g->kT;
     }
     P.ntn = g->Cin / cfg.bn;

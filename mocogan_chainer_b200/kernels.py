@@ -49,11 +49,12 @@ _ws_cache = {}
 
 
 def workspace(nbytes, device):
-    """Per-(device, stream) scratch for the column reductions (allocated once; kernels never allocate)."""
+    """Per-(device, stream) scratch for the column reductions (allocated once; kernels never allocate).  ZERO-FILLED at
+    allocation: the reductions keep their slot sums and ticket counter in it and hand it back zeroed (mcg.h)."""
     key = (device, torch.cuda.current_stream().cuda_stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        buf = torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
 
@@ -212,6 +213,19 @@ def loss_gen(y_i, y_v, t_fake, N, Cc, use_ce, loss, gy_i, gy_v):
 def adam_step(p, g, m, v, p_bf16, alpha, beta1, beta2, eps, wd, grad_scale, t_ptr):
     check(lib().mcg_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), p.numel(), alpha, beta1, beta2, eps, wd,
                               grad_scale, ptr(t_ptr), stream()), "mcg_adam_step")
+
+
+def fill_zero(t):
+    """Zero-fills a contiguous tensor on the current stream (cudaMemsetAsync — no kernel)."""
+    assert t.is_contiguous()
+    check(lib().mcg_fill_zero(ptr(t), t.numel() * t.element_size(), stream()), "mcg_fill_zero")
+
+
+def pad_channels(src, dst):
+    """dst[..., :C] = src, dst[..., C:] = 0 for channels-last tensors of equal leading shape."""
+    C_, Cp = src.shape[-1], dst.shape[-1]
+    assert src.is_contiguous() and dst.is_contiguous() and src.dtype == dst.dtype and src.numel() // C_ == dst.numel() // Cp
+    check(lib().mcg_pad_channels(ptr(src), ptr(dst), src.numel() // C_, C_, Cp, dt_code(src), stream()), "mcg_pad_channels")
 
 
 def cast_bf16(src, dst):

@@ -38,7 +38,7 @@ def test_version_and_error_string_without_gpu():
     lib = _lib.load()
     assert lib.mcg_version() == 100
     assert isinstance(lib.mcg_last_error(), bytes)
-    assert lib.mcg_colreduce_workspace_bytes(1000, 64) == 592 * 2 * 64 * 4
+    assert lib.mcg_colreduce_workspace_bytes(1000, 64) == 16 * 2 * 64 * 4 + 256    # 16 slot rows + the ticket counter
 
 
 def test_shape_errors_are_reported_before_any_launch():

@@ -223,3 +223,48 @@ def test_log_tensorboard_hook_writes_eval_mode_grid_frames(tmp_path):
     w.add_image("00th frame", img, 1)
     w.add_scalar("loss:ImageGenerator", 0.5, 1)
     assert (tmp_path / "runs" / "00th_frame_000001.png").exists() and (tmp_path / "runs" / "scalars.jsonl").exists()
+
+
+@pytest.mark.parametrize("dtype_mode,nf,tol", [("fp32", 8, 1e-5), ("bf16", 64, 3e-2)])
+def test_generator128_extension_matches_composed_oracle_ops(dtype_mode, nf, tol):
+    """model/net128.py (EXTENSION, parity unpinned by the reference — it cannot emit 128x128): the six-stage generator
+    against the oracle's GRU / deconvolution / BatchNorm restatements composed the same way.  bf16: six chained bf16
+    layers compared on tanh's absolute scale, like x_fake in test_step_gpu.py (FORWARD_SLACK)."""
+    from mocogan_chainer_b200 import chainer
+    from mocogan_chainer_b200 import random as mrandom
+    from mocogan_chainer_b200.model.net128 import ImageGenerator128
+    from oracle import chainer_ops as ops
+    from oracle import mocogan_ref as ref
+    chainer.config.compute_dtype = dtype_mode
+    np.random.seed(4)
+    T, N = 4, 3
+    G = ImageGenerator128(50, 10, 6, 3, nf, T)
+    G.arena()
+    assert sorted(G._children) == ["bn1", "bn2", "bn3", "bn4", "bn5", "dc1", "dc2", "dc3", "dc4", "dc5", "dc6", "g0"]
+    P = {path.lstrip("/"): p.data.float().cpu().numpy().astype(np.float64) for path, p in G.namedparams()}
+    assert P["dc1/W"].shape == (60, nf * 16, 4, 4) and P["dc6/W"].shape == (nf, 3, 4, 4)
+    lat = ref.ImageGenerator.draw_latents(np.random.default_rng(9), N, 50, 10, 6, T, np.float32)
+    # the oracle's motion path (net.py:61-107 restated), then six deconvolution stages
+    g0 = {k[3:]: v for k, v in P.items() if k.startswith("g0/")}
+    zl = np.eye(6)[lat["labels"]]
+    h, hs = lat["h0"].astype(np.float64), []
+    for t in range(T):
+        h, _ = ops.gru_step_fwd(g0, h, np.concatenate((zl, lat["eps"][t]), axis=1))
+        hs.append(h)
+    z = np.concatenate((np.tile(lat["zc"][None], (T, 1, 1)), np.stack(hs)), axis=2).reshape(T * N, 60, 1, 1)
+    x = z
+    for i in range(1, 7):
+        s, p = ((1, 1), (0, 0)) if i == 1 else ((2, 2), (1, 1))
+        y = ops.deconv_nd_fwd(x, P["dc%d/W" % i], P["dc%d/b" % i], s, p)
+        x = np.maximum(ops.batchnorm_fwd(y, P["bn%d/gamma" % i], P["bn%d/beta" % i])[0], 0) if i < 6 else np.tanh(y)
+    want = x.reshape(T, N, 3, 128, 128)
+    r = {"t": 0, "noise_i_real": [], "noise_v_real": [], "noise_i_fake": [], "noise_v_fake": [], "latents": lat}
+    mrandom.set_source(mrandom.InjectedRandom(r))
+    with chainer.no_backprop_mode():
+        got, labels = G(N)
+    torch.cuda.synchronize()
+    assert tuple(got.shape) == (T, N, 3, 128, 128)
+    err = np.abs(got.data.float().cpu().numpy() - want).max() / np.abs(want).max()
+    assert err < tol, err
+    assert abs(G.forward_gflop_per_frame() - 2 * 16 * (60 * 16 * nf + 16 * nf * 8 * nf * 16 + 8 * nf * 4 * nf * 64 + 4 * nf * 2 * nf * 256
+                                                         + 2 * nf * nf * 1024 + nf * 3 * 4096) / 1e9) < 1e-9
