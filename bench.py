@@ -235,6 +235,46 @@ def time_conv_layers(K, torch, peaks):
     return rows
 
 
+def time_narrow_layers(K, torch, peaks):
+    """The 3-channel image layers (Dv.dc1, Di.dc1, G.dc5): 1.5 % of the step's FLOPs but HBM/L2-bound (Dv.dc1 writes 29.8 M
+    outputs).  Each call timed ALONE; achieved = algorithmic bytes (input + output tensors of the call, once each) / time
+    against the measured copy bandwidth.  A call includes its layout passes (row interleave / weight pad / depth-to-space)."""
+    layers = [  # name, N, Cin, Cout, in_sp, k, s, p, calls per step (fprop, dgrad, wgrad) of the conv geometry
+        ("Dv.dc1", 35, 3, 64, (16, 64, 64), (4, 4, 4), (1, 2, 2), (0, 1, 1), (2, 1, 2)),
+        ("Di.dc1", 35, 3, 64, (1, 64, 64), (1, 4, 4), (1, 2, 2), (0, 1, 1), (2, 1, 2)),
+        ("G.dc5", 560, 3, 64, (1, 64, 64), (1, 4, 4), (1, 2, 2), (0, 1, 1), (1, 1, 1)),
+    ]
+    rows = []
+    for name, N, Cin, Cout, in_sp, k, s, p, calls in layers:
+        g = K.make_geom(N, Cin, Cout, in_sp, k, s, p)
+        x = torch.randn((N,) + in_sp + (Cin,), device="cuda").bfloat16()
+        w = (torch.randn((Cout,) + k + (Cin,), device="cuda") * 0.05).bfloat16()
+        gy = torch.randn((N, g.To, g.Ho, g.Wo, Cout), device="cuda").bfloat16()
+        y, dx = torch.empty_like(gy), torch.empty_like(x)
+        dw = torch.zeros(w.shape, device="cuda")
+        ws = K.conv_fprop(g, x, w, None, y, K.IMPL_TC)
+        xb, yb = x.numel() * 2, gy.numel() * 2
+        fns = (("fprop", lambda: K.conv_fprop(g, x, w, None, y, K.IMPL_TC, ws=ws), xb + yb),
+               ("dgrad", lambda: K.conv_dgrad(g, gy, w, None, dx, K.IMPL_TC), xb + yb),
+               ("wgrad (x layout reused from fprop)", lambda: K.conv_wgrad(g, x, gy, dw, K.IMPL_TC, ws=ws, cols_valid=True), xb + yb))
+        for (kind, fn, nbytes), ncalls in zip(fns, calls):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            rows.append({"kernel": "conv_%s" % kind, "layer": name, "ms": ms, "calls_per_step": ncalls,
+                         "algorithmic_mb": nbytes / 1e6, "gb_per_s": nbytes / ms / 1e6,
+                         "frac_of_hbm_peak": nbytes / ms / 1e6 / peaks["hbm_gbs"]})
+    return rows
+
+
 def time_stream_kernels(K, torch, peaks):
     """HBM-bound passes of the step ("which roofline": K5/K8/K10/K11), each timed ALONE with CUDA events on
     tensors larger than L2 (the generator's widest BatchNorm layer, G.bn4: 35*16 frames x 32x32 pixels x 64 channels =
@@ -505,10 +545,11 @@ def run_ours(args):
         except ImportError:
             gen128 = None
 
-    layer_rows, stream_rows, dominant, cpu = None, None, None, None
+    layer_rows, stream_rows, narrow_rows, dominant, cpu = None, None, None, None, None
     if rank == 0:
         layer_rows = time_conv_layers(K, torch, peaks)
         stream_rows = time_stream_kernels(K, torch, peaks)
+        narrow_rows = time_narrow_layers(K, torch, peaks)
         tot = {}
         for r in layer_rows:
             tot[(r["kernel"], r["layer"])] = r["ms"] * r["calls_per_step"]
@@ -560,6 +601,7 @@ def run_ours(args):
                               "tc_conv_ms_per_step_isolated": conv_ms,
                               "tc_conv_frac_of_burst_isolated": sum(r["gflop"] * r["calls_per_step"] for r in layer_rows) / conv_ms / peaks["bf16_burst"]},
                      "layers": layer_rows,
+                     "narrow_layers": narrow_rows,
                      "hbm_kernels": {"peak_gb_per_s": peaks["hbm_gbs"], "peak_source": peaks["src"] + " (copy bandwidth)",
                                      "kernels": stream_rows}},
         "cpu_baseline": cpu,

@@ -74,6 +74,9 @@ class VideoGrad(object):
     __radd__ = __add__
 
 
+_ONES = {}
+
+
 def _accumulate(a, b):
     if a is None:
         return b
@@ -139,7 +142,14 @@ class Variable(object):
         if self.creator_node is None:
             return
         if self._grad is None:
-            self._grad = torch.ones_like(self.data)
+            # a scalar loss seeds 1; the constant is made once per device (no fill kernel per backward pass)
+            if self.data.dim() == 0 and self.data.dtype == torch.float32:
+                key = str(self.data.device)
+                if key not in _ONES:
+                    _ONES[key] = torch.ones((), device=self.data.device)
+                self._grad = _ONES[key]
+            else:
+                self._grad = torch.ones_like(self.data)
         grads = {id(self): self._grad}
         keep = {id(self): self}
         heap, seen = [], set()

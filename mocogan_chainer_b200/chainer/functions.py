@@ -427,7 +427,9 @@ class GRUSequence(FunctionNode):
 
     def backward(self, idx, gys):
         T, N, H, Zc = self.dims
-        gz = gys[0].reshape(T * N, Zc + H).float().contiguous()
+        # the gradient arrives as a 60-channel slice of dc1's zero-padded bf16 storage: one gather pass makes it the
+        # contiguous fp32 matrix the GRU kernel reads
+        gz = as_physical(gys[0].reshape(T * N, Zc + H), torch.float32).reshape(T * N, Zc + H)
         K.gru_backward([p.store for p in self.inputs], [p.gstore for p in self.inputs], self.labels, self.L, self.eps,
                        self.cache, gz, T, N, H, Zc)
         return tuple(True for _ in idx)

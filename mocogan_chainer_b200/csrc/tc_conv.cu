@@ -66,6 +66,7 @@ struct TcParams {
   // one contiguous run: tap-group index i (skip_per_kt taps each) reads frame t*a_mul_t + a_add_t + skip_dt0 + i*skip_dts.
   int skip_t, skip_per_kt[8], skip_nkt, skip_dt0, skip_dts, skip_aT;   // skip_per_kt: per stride class
   int str_rounds, str_rem_per; long long str_rem0;   // strided: full rounds of groups, then total - str_rem0 left-over units dealt str_rem_per per CTA
+  int win, win_T;   // window-view A operand of the 3-channel layers (see TcWin): TMA coordinates (0, w, h, n*win_T + t, 0)
   int strided;  // > 0: CTA c takes the unit groups c, c + grid, c + 2*grid, ... of `strided` units each (boxes cost
                 // different numbers of K steps once taps are skipped; contiguous ranges would be frame-coherent and uneven)
   int box_tn;   // 1: boxes are numbered (w, h, n, t) — frames slowest — so the MT boxes of a step share their frame and skip alike
@@ -80,6 +81,14 @@ struct TcParams {
 __device__ int g_tc_error = 0;
 
 constexpr int kTcThreads = 320;      // warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue (two per TMEM lane quarter)
+// The plain kernel can run a SECOND producer thread (warp 10; -DMCG_TC_PROD2=1): ncu's source page shows the MMA thread
+// waiting for data 44 % of its samples while the producer is issuing, not waiting, 68 % of its own, which looked like an
+// issue-bound producer.  Measured (A/B of two builds, every config-2 layer and the whole step): no difference — the
+// kernels sit on the L2 -> SM ceiling (~13.5-14.4 TB/s delivered), not on the producer.  Kept, off.
+#ifndef MCG_TC_PROD2
+#define MCG_TC_PROD2 0
+#endif
+constexpr int kTcConvThreads = MCG_TC_PROD2 ? 352 : 320;
 constexpr int kEpiThreads = 256;
 constexpr int A_BYTES = 128 * 128;  // 128 rows x 64 bf16
 
@@ -356,7 +365,7 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& P, void* __rest
 }
 
 template <int MODE, int BN, int MT, int STAGES>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(kTcConvThreads, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                 const __grid_constant__ CUtensorMap mapB,
                                                                 const __grid_constant__ TcParams P, void* __restrict__ out,
                                                                 const float* __restrict__ bias) {
@@ -398,14 +407,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
   const uint32_t tfull_a = smem_u32(&tfull_bar[0]), tempty_a = smem_u32(&tempty_bar[0]);
   const uint32_t sfull_a = smem_u32(&sfull_bar[0]), sempty_a = smem_u32(&sempty_bar[0]);
 
-  if (warp == 0) {
+  if (warp == 0 || warp == 10) {
     // ================================================= TMA producer =========================================
-    // ONE elected thread; the loop is instruction-bound, so everything per K step is strength-reduced: no divisions,
-    // tap / slab decode hoisted, barrier and stage addresses advanced incrementally.
-    if (elect_one()) {
+    // One elected thread per producer warp; the loop is instruction-bound, so everything per K step is strength-reduced:
+    // no divisions, tap / slab decode hoisted, barrier and stage addresses advanced incrementally.  With two producers
+    // (static schedules only) both walk the whole step sequence and each issues the steps of its own parity.
+    const uint32_t nprod = (MCG_TC_PROD2 && !P.dyn) ? 2u : 1u, prod = warp == 0 ? 0u : 1u;
+    if (prod < nprod && elect_one()) {
       const uint64_t map_a = reinterpret_cast<uint64_t>(&mapA), map_b = reinterpret_cast<uint64_t>(&mapB);
       TcSegIter<MODE, MT> iter;
       TcSeg sg;
+      uint32_t kstep = 0;   // ring steps issued by either producer so far
       int s = 0;
       uint32_t ph = 1;   // ring slot and the parity its `empty` barrier is waited with
       uint32_t stage_a = smem_a, full_s = full_a, empty_s = empty_a;
@@ -470,19 +482,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
             const TcTap tp = P.taps[j];
             const int kcol = tp.kidx * P.Cin;
             for (int c = 0; c < chunks; ++c) {
+              if ((kstep++ & (nprod - 1)) == prod) {
               if (!mbar_wait_a(empty_s, ph, err)) { alive = false; break; }
               mbar_expect_tx_a(full_s, tx_bytes);
 #pragma unroll
               for (int m = 0; m < MT; ++m)
-                if (m < sg.nlive)
-                  tma_load_5d_a(stage_a + m * A_BYTES, map_a, full_s, c * 64, bx[m].w0 + tp.dw, bx[m].h0 + tp.dh,
-                                bx[m].t0 + tp.dt, bx[m].n0);
+                if (m < sg.nlive) {
+                  if (MODE == kFprop && P.win)
+                    tma_load_5d_a(stage_a + m * A_BYTES, map_a, full_s, 0, bx[m].w0, bx[m].h0,
+                                  bx[m].n0 * P.win_T + bx[m].t0 + tp.dt, 0);
+                  else
+                    tma_load_5d_a(stage_a + m * A_BYTES, map_a, full_s, c * 64, bx[m].w0 + tp.dw, bx[m].h0 + tp.dh,
+                                  bx[m].t0 + tp.dt, bx[m].n0);
+                }
               if (MODE == kFprop) {
                 tma_load_2d_a(stage_a + MT * A_BYTES, map_b, full_s, kcol + c * 64, ncol0);
               } else {
 #pragma unroll
                 for (int sl = 0; sl < BN / 64; ++sl)
                   tma_load_2d_a(stage_a + MT * A_BYTES + sl * 8192, map_b, full_s, kcol + ncol0 + sl * 64, c * 64);
+              }
               }
               ++s; stage_a += STAGE_BYTES; full_s += 8; empty_s += 8;
               if (s == STAGES) { s = 0; ph ^= 1; stage_a = smem_a; full_s = full_a; empty_s = empty_a; }
@@ -503,15 +522,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
           const int wlim = P.nbw * P.BW, hlim = P.nbh * P.BH, tlim = P.nbt * P.BT;
           const int BWs = P.BW, BHs = P.BH, BTs = P.BT, BBs = P.BB, mw = P.a_mul_w, mh = P.a_mul_h, mt_ = P.a_mul_t;
           for (int kb = 0; kb < sg.nk; ++kb) {
+            if ((kstep++ & (nprod - 1)) == prod) {
             if (!mbar_wait_a(empty_s, ph, err)) { alive = false; break; }
             mbar_expect_tx_a(full_s, STAGE_BYTES);
             const int aw = pb.w0 * mw, ah = pb.h0 * mh, at = pb.t0 * mt_;
 #pragma unroll
-            for (int sl = 0; sl < MT * 2; ++sl)
-              tma_load_5d_a(stage_a + sl * 8192, map_a, full_s, sc[sl], aw + sw[sl], ah + sh[sl], at + st_[sl], pb.n0);
+            for (int sl = 0; sl < MT * 2; ++sl) {
+              if (P.win)      // a dummy slab (sc = Cin) asks for a frame past the end of the tensor: zero fill
+                tma_load_5d_a(stage_a + sl * 8192, map_a, full_s, 0, pb.w0, pb.h0,
+                              sc[sl] < P.Cin ? pb.n0 * P.win_T + pb.t0 + st_[sl] : 0x3fffffff, 0);
+              else
+                tma_load_5d_a(stage_a + sl * 8192, map_a, full_s, sc[sl], aw + sw[sl], ah + sh[sl], at + st_[sl], pb.n0);
+            }
 #pragma unroll
             for (int sl = 0; sl < BN / 64; ++sl)
               tma_load_5d_a(stage_a + MT * A_BYTES + sl * 8192, map_b, full_s, ncol0 + sl * 64, pb.w0, pb.h0, pb.t0, pb.n0);
+            }
             ++s; stage_a += STAGE_BYTES; full_s += 8; empty_s += 8;
             if (s == STAGES) { s = 0; ph ^= 1; stage_a = smem_a; full_s = full_a; empty_s = empty_a; }
             pb.w0 += BWs;   // next pixel box, carried by hand
@@ -821,6 +847,28 @@ static int act_map(CUtensorMap* m, const void* base, int C, int W, int H, int T,
   return get_map(m, base, 5, dims, str, box, es);
 }
 
+// Window view of the 3-channel image layers (kH = kW = 4, stride 2).  x is re-laid once per call as
+//   xk[frame][ho][wq][kh = 4][c4]   = x[frame][ho*sH + kh - pH][wq - pW][c]   (zero border, channels padded to 4)
+// i.e. the kH input rows an output row reads are interleaved per pixel (2x the image, 38 MB for Dv.dc1).  The 4 px x 4 kh
+// x 4 ch = 64 values an output pixel (ho, wo) reads are then 128 CONTIGUOUS bytes starting at pixel wo*sW, so the map
+//   dims (64, Wo, Ho, frames)   strides (-, sW px = 64 B, row, frame)        [windows overlap along wo: loads only]
+// with box (64, BW, BH, BF) lands [pixel][(kw, kh, c4) = 64] rows of 128 B in shared memory — exactly the K-major SW128
+// A tile of a 64-channel layer.  The layer then runs through the implicit-GEMM kernels as a "1 x 1 x kT-tap convolution
+// over 64 channels", and the M x 192 im2col matrix (179 MB for Dv.dc1, written and re-read on every call) is gone.
+struct TcWin {
+  const void* xk;
+  int Wq, Ho, Wo, frames, T;    // T = frames per sample (merged coordinate = n*T + t)
+  int sW;
+};
+static int win_map(CUtensorMap* m, const TcWin& w, int bw, int bh, int bf) {
+  uint64_t dims[5] = {64, (uint64_t)w.Wo, (uint64_t)w.Ho, (uint64_t)w.frames, 1};
+  const uint64_t row = (uint64_t)w.Wq * 32;
+  uint64_t str[4] = {(uint64_t)w.sW * 32, row, (uint64_t)w.Ho * row, (uint64_t)w.frames * w.Ho * row};
+  uint32_t box[5] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bf, 1};
+  uint32_t es[5] = {1, 1, 1, 1, 1};
+  return get_map(m, w.xk, 5, dims, str, box, es);
+}
+
 struct Box { int w, h, t, b; };
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // split `target` (a power of two) pixels into a (w,h,t,b) box minimising padded volume; prefer wide boxes
@@ -952,7 +1000,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
     if (e != cudaSuccess) MCG_FAIL((int)e, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
     configured = true;
   }
-  pdl(tc_conv_kernel<MODE, BN, MT, STAGES>, grid, kTcThreads, smem, st)(ma, mb, P, out, bias);
+  pdl(tc_conv_kernel<MODE, BN, MT, STAGES>, grid, kTcConvThreads, smem, st)(ma, mb, P, out, bias);
   MCG_CHECK_LAUNCH(who);
   return 0;
 }
@@ -1490,7 +1538,7 @@ bool tc_supported(const mcg_conv_geom* g) {
 }
 
 int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void* out, const float* bias, int out_dtype,
-            cudaStream_t st, int kreal = 0, int planar_chunk = 0, int planar_cols = 0, int wrows = 0) {
+            cudaStream_t st, int kreal = 0, int planar_chunk = 0, int planar_cols = 0, int wrows = 0, const TcWin* win = nullptr) {
   const char* who = mode == kFprop ? "mcg_conv_fprop(tc)" : mode == kDgrad ? "mcg_conv_dgrad(tc)" : "mcg_conv_wgrad(tc)";
   if (!tc_supported(g)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: needs Cin,Cout %% 64 == 0, stride <= 2, <= 64 taps", who);
   TcParams P;
@@ -1517,7 +1565,9 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
   int rc;
   if (mode == kFprop) {
     // a = x (N,Ti,Hi,Wi,Cin), b = w bf16 (Cout, taps*Cin), out = y (N,To,Ho,Wo,Cout)
-    Box bx = choose_box(128, g->Wo, g->Ho, g->To, g->N);
+    // (window view: frames of different samples are not a box of the merged frame axis, so 3-D layers take one sample per box)
+    Box bx = (win && win->T > 1) ? choose_box(128, g->Wo, g->Ho, g->To, 1) : choose_box(128, g->Wo, g->Ho, g->To, g->N);
+    if (win) { P.win = 1; P.win_T = win->T; }
     P.BW = bx.w; P.BH = bx.h; P.BT = bx.t; P.BB = bx.b;
     P.nbw = ceil_div(g->Wo, bx.w); P.nbh = ceil_div(g->Ho, bx.h); P.nbt = ceil_div(g->To, bx.t); P.nbb = ceil_div(g->N, bx.b);
     P.EW = g->Wo; P.EH = g->Ho; P.ET = g->To; P.EN = g->N;
@@ -1535,7 +1585,7 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
     P.nboxes = P.nbw * P.nbh * P.nbt * P.nbb;
     double plain_cost = 0;
     const TileCfg cfg = pick_tile(kFprop, P.nboxes, 1, g->Cout, taps * P.chunks, &plain_cost);
-    if (g->kT >= 2 && g->sT == 1 && !planar_chunk) {
+    if (g->kT >= 2 && g->sT == 1 && !planar_chunk && !win) {
       const TrPlan tr = plan_tr(g->Wo, g->Ho, g->To, g->N, g->Cout, 1, g->kH * g->kW, P.chunks, g->kT);
       if (tr_wanted(tr, plain_cost)) {
         const Box tb = tr.bx;
@@ -1558,7 +1608,11 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
         return launch_tr_cfg<kFprop>(tr.bn, tr.mt, ma, mb, P, grid, out, bias, st, who);
       }
     }
-    if ((rc = act_map(&ma, a, g->Cin, g->Wi, g->Hi, g->Ti, g->N, bx.w, bx.h, bx.t, bx.b, g->sW, g->sH, g->sT))) return rc;
+    if (win) {
+      if ((rc = win_map(&ma, *win, bx.w, bx.h, win->T > 1 ? bx.t : bx.b))) return rc;
+    } else if ((rc = act_map(&ma, a, g->Cin, g->Wi, g->Hi, g->Ti, g->N, bx.w, bx.h, bx.t, bx.b, g->sW, g->sH, g->sT))) {
+      return rc;
+    }
     if (g->kT > 1 && g->pT > 0 && !tc_env_int("MCG_TC_NOSKIP")) {   // temporal zero padding: edge boxes skip the taps that read only padding
       P.skip_t = 1; P.skip_per_kt[0] = g->kH * g->kW; P.skip_nkt = g->kT; P.skip_dt0 = 0; P.skip_dts = 1; P.skip_aT = g->Ti;
       P.box_tn = tc_env_int("MCG_TC_STRIDED") > 0 || (tc_env_int("MCG_TC_STRIDED") == 0 && cfg.bn == 64);
@@ -1667,7 +1721,8 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
   }
   // ---- wgrad: a = x (N,Ti,Hi,Wi,Cin), b = dy (N,To,Ho,Wo,Cout), out = dw fp32 (Cout, taps*Cin), accumulated
   {
-    Box bx = choose_box(64, g->Wo, g->Ho, g->To, g->N);
+    Box bx = (win && win->T > 1) ? choose_box(64, g->Wo, g->Ho, g->To, 1) : choose_box(64, g->Wo, g->Ho, g->To, g->N);
+    if (win) { P.win = 1; P.win_T = win->T; }
     P.BW = bx.w; P.BH = bx.h; P.BT = bx.t; P.BB = bx.b;
     P.nbw = ceil_div(g->Wo, bx.w); P.nbh = ceil_div(g->Ho, bx.h); P.nbt = ceil_div(g->To, bx.t); P.nbb = ceil_div(g->N, bx.b);
     P.a_mul_w = g->sW; P.a_mul_h = g->sH; P.a_mul_t = g->sT; P.a_add_w = -g->pW; P.a_add_h = -g->pH; P.a_add_t = -g->pT;
@@ -1691,7 +1746,11 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
     P.ntn = g->Cout / cfg.bn;
     P.ntiles = mgroups * P.ntn;
     const int ctas = split_units(P, (long long)P.ntiles * P.total_boxes, 8);   // at least 8 K steps per CTA
-    if ((rc = act_map(&ma, a, g->Cin, g->Wi, g->Hi, g->Ti, g->N, bx.w, bx.h, bx.t, bx.b, g->sW, g->sH, g->sT))) return rc;
+    if (win) {
+      if ((rc = win_map(&ma, *win, bx.w, bx.h, win->T > 1 ? bx.t : bx.b))) return rc;
+    } else if ((rc = act_map(&ma, a, g->Cin, g->Wi, g->Hi, g->Ti, g->N, bx.w, bx.h, bx.t, bx.b, g->sW, g->sH, g->sT))) {
+      return rc;
+    }
     if ((rc = act_map(&mb, b, g->Cout, g->Wo, g->Ho, g->To, g->N, bx.w, bx.h, bx.t, bx.b, 1, 1, 1))) return rc;
     return launch_tc_cfg<kWgrad>(cfg, ma, mb, P, ctas, out, nullptr, st, who);
   }
@@ -1951,19 +2010,90 @@ static bool merged_geom(const mcg_conv_geom* g, MergedGeom* G) {
 
 static long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 
+// ---- window-view path of the 3-channel layers (see TcWin): layout helpers -----------------------------------------
+// xk[f][ho][wq][kh][0..4) = x[f][ho*sH + kh - pH][wq - pW][c] inside the image and for c < C, 0 elsewhere
+__global__ void __launch_bounds__(256) interleave_rows_kernel(const __nv_bfloat16* __restrict__ x, uint4* __restrict__ xk,
+                                                              long long frames, int H, int W, int C, int Ho, int Wq, int sH,
+                                                              int pH, int pW) {
+  pdl_enter();
+  // one thread per (frame, ho, wq): reads the pixel from the kH = 4 rows (consecutive threads read consecutive pixels of a
+  // row) and writes its 32 contiguous bytes [kh][c4]
+  const long long total = frames * Ho * Wq;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int wq = (int)(i % Wq);
+    const long long r = i / Wq;
+    const int ho = (int)(r % Ho);
+    const long long f = r / Ho;
+    const int w = wq - pW;
+    __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = __float2bfloat16_rn(0.f);
+    if ((unsigned)w < (unsigned)W) {
+#pragma unroll
+      for (int kh = 0; kh < 4; ++kh) {
+        const int h = ho * sH + kh - pH;
+        if ((unsigned)h < (unsigned)H) {
+          const __nv_bfloat16* src = x + ((f * H + h) * (long long)W + w) * C;
+          for (int c = 0; c < C; ++c) v[kh * 4 + c] = src[c];
+        }
+      }
+    }
+    xk[2 * i] = *reinterpret_cast<const uint4*>(v);
+    xk[2 * i + 1] = *reinterpret_cast<const uint4*>(v + 8);
+  }
+}
+// w4[co][kt][kw][kh][0..4) = w[co][kt][kh][kw][c < C], 0 beyond: the K order of the window rows
+__global__ void pad_w4_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ w4, int rows_kt, int C) {
+  pdl_enter();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows_kt * 64; i += gridDim.x * blockDim.x) {
+    const int c = i & 3, kh = (i >> 2) & 3, kw = (i >> 4) & 3, rk = i >> 6;
+    w4[i] = c < C ? w[((long long)rk * 16 + kh * 4 + kw) * C + c] : __float2bfloat16_rn(0.f);
+  }
+}
+// dw[co][kt][kh][kw][c] += dw4[co][kt][kw][kh][c]  (the padded channel is dropped); atomic: real and fake branches share dw
+__global__ void unpad_dw4_kernel(const float* __restrict__ dw4, float* __restrict__ dw, int rows_kt, int C) {
+  pdl_enter();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows_kt * 16 * C; i += gridDim.x * blockDim.x) {
+    const int c = i % C, tap = (i / C) & 15, rk = i / (16 * C);
+    const int kh = tap >> 2, kw = tap & 3;
+    atomicAdd(dw + i, dw4[(rk * 16 + kw * 4 + kh) * 4 + c]);
+  }
+}
+static bool win_geom_ok(const mcg_conv_geom* g) {
+  return g->Cin <= 4 && g->Cout % 64 == 0 && g->kH == 4 && g->kW == 4 && g->sW == 2 && g->sH >= 1 && g->sH <= 2 && g->sT == 1 &&
+         g->pT == 0 && g->kT <= 16 && !tc_env_int("MCG_TC_NOWIN");
+}
+struct WinLayout { int Wq; size_t xq_bytes, w4_bytes, dw4_bytes; };
+static WinLayout win_layout(const mcg_conv_geom* g) {
+  WinLayout L;
+  L.Wq = g->Wi + g->pW > (g->Wo - 1) * g->sW + g->kW ? g->Wi + g->pW : (g->Wo - 1) * g->sW + g->kW;
+  L.xq_bytes = (size_t)round_up((long long)g->N * g->Ti * g->Ho * L.Wq * 32, 1024);
+  L.w4_bytes = (size_t)round_up((long long)g->Cout * g->kT * 64 * 2, 1024);
+  L.dw4_bytes = (size_t)round_up((long long)g->Cout * g->kT * 64 * 4, 1024);
+  return L;
+}
+
 bool tc_small_supported(const mcg_conv_geom* g) {
   return g->Cin <= 16 && g->Cout % 64 == 0 && g->sT <= 2 && g->sH <= 2 && g->sW <= 2 && g->kT * g->kH * g->kW <= 64 &&
          g->kW % 4 == 0;
 }
 size_t tc_small_workspace(const mcg_conv_geom* g) {
+  // the largest of what the paths this geometry can take need (tc_conv_small picks by the same predicates)
   const long long M = (long long)g->N * g->To * g->Ho * g->Wo;
   const long long K = (long long)g->kT * g->kH * g->kW * g->Cin, Kp = round_up(K, 64);
-  size_t need = (size_t)(round_up(M * Kp * 2, 1024) + round_up((long long)g->Cout * Kp * 2, 1024) + 4096);
+  const size_t cols_need = (size_t)(round_up(M * Kp * 2, 1024) + round_up((long long)g->Cout * Kp * 2, 1024) + 4096);
   MergedGeom G;
-  if (merged_geom(g, &G)) {   // dgrad: Zm (one 64-column row per stride cell) + the merged weights
+  const bool merged = merged_geom(g, &G) && !getenv("MCG_NO_MERGED_DGRAD"), win = win_geom_ok(g);
+  size_t need = 0;
+  if (win) {                       // fprop / wgrad read a re-laid copy of x through a window view: no im2col matrix
+    const WinLayout L = win_layout(g);
+    need = L.xq_bytes + L.w4_bytes + L.dw4_bytes + 4096;
+  }
+  if (!win || !merged) need = cols_need > need ? cols_need : need;   // im2col GEMM (fprop / wgrad) or Z = dy.w^T + col2im (dgrad)
+  if (merged) {                    // dgrad: Zm (one 64-column row per stride cell) + the merged weights
     const long long cells = (long long)g->N * ceil_div(g->Ti, g->sT) * ceil_div(g->Hi, g->sH) * ceil_div(g->Wi, g->sW);
-    const size_t merged = (size_t)(round_up(cells * 128, 1024) + round_up(64LL * G.nT * G.nH * G.nW * g->Cout * 2, 1024) + 4096);
-    if (merged > need) need = merged;
+    const size_t m = (size_t)(round_up(cells * 128, 1024) + round_up(64LL * G.nT * G.nH * G.nW * g->Cout * 2, 1024) + 4096);
+    if (m > need) need = m;
   }
   return need;
 }
@@ -1984,7 +2114,7 @@ int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b
     // a = dy (N,To,Ho,Wo,Cout), b = w bf16 (Cout,taps,Cin), out = dx (N,Ti,Hi,Wi,Cin):
     //   Z[M][Kp] = dy[M][Cout] . wt[Kp][Cout]^T  (tcgen05 GEMM over the line of M output pixels), then col2im.
     MergedGeom G;
-    if (merged_geom(g, &G) && !getenv("MCG_NO_MERGED_DGRAD")) {
+    if (merged_geom(g, &G) && !getenv("MCG_NO_MERGED_DGRAD")) {   // (same predicate as tc_small_workspace)
       const int L = ceil_div(g->Ti, g->sT), I = ceil_div(g->Hi, g->sH), J = ceil_div(g->Wi, g->sW);
       const long long cells = (long long)g->N * L * I * J;
       __nv_bfloat16* zm = reinterpret_cast<__nv_bfloat16*>(base);
@@ -2013,6 +2143,37 @@ int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b
     pdl(col2im_line_kernel, (unsigned)lines, 128, smem, st)(cols, bias, out, out_dtype == MCG_F32, M, g->Cin, g->Ti, g->Hi, g->Wi,
                                                            g->To, g->Ho, g->Wo, g->kT, g->kH, g->kW, g->sT, g->sH, g->sW, g->pT,
                                                            g->pH, g->pW);
+    MCG_CHECK_LAUNCH(who);
+    return 0;
+  }
+  if (win_geom_ok(g)) {
+    // fprop / wgrad through the window view (TcWin): pad x once (reused by wgrad: cols_valid), then the implicit-GEMM
+    // kernels with kT taps of 64 "channels" = (kh, kw, c4)
+    const WinLayout L = win_layout(g);
+    uint8_t* xq = base;
+    __nv_bfloat16* w4 = reinterpret_cast<__nv_bfloat16*>(base + L.xq_bytes);
+    float* dw4 = reinterpret_cast<float*>(base + L.xq_bytes + L.w4_bytes);
+    const long long frames = (long long)g->N * g->Ti;
+    if (frames * g->Ho > 0x7fffffffLL) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: too many rows", who);
+    if (!cols_valid) {
+      long long nb = (frames * g->Ho * L.Wq + 255) / 256;
+      if (nb > (long long)num_sms() * 16) nb = (long long)num_sms() * 16;
+      pdl(interleave_rows_kernel, (unsigned)nb, 256, 0, st)((const __nv_bfloat16*)a, reinterpret_cast<uint4*>(xq), frames, g->Hi,
+                                                            g->Wi, g->Cin, g->Ho, L.Wq, g->sH, g->pH, g->pW);
+      MCG_CHECK_LAUNCH(who);
+    }
+    const TcWin win{xq, L.Wq, g->Ho, g->Wo, (int)frames, g->Ti, g->sW};
+    mcg_conv_geom g2 = {g->N, 64, g->Cout, g->Ti, g->Ho, g->Wo, g->To, g->Ho, g->Wo, g->kT, 1, 1, 1, 1, 1, 0, 0, 0};
+    const int rows_kt = g->Cout * g->kT, rows_taps = rows_kt * 16;
+    if (mode == kFprop) {
+      pdl(pad_w4_kernel, 32, 256, 0, st)((const __nv_bfloat16*)b, w4, rows_kt, g->Cin);
+      MCG_CHECK_LAUNCH(who);
+      return tc_conv(kFprop, &g2, xq, w4, out, bias, out_dtype, st, 0, 0, 0, 0, &win);
+    }
+    cudaError_t e = cudaMemsetAsync(dw4, 0, (size_t)rows_taps * 4 * sizeof(float), st);
+    if (e != cudaSuccess) MCG_FAIL((int)e, "%s: cudaMemsetAsync: %s", who, cudaGetErrorString(e));
+    if ((rc = tc_conv(kWgrad, &g2, xq, b, dw4, nullptr, MCG_F32, st, 0, 0, 0, 0, &win))) return rc;
+    pdl(unpad_dw4_kernel, 32, 256, 0, st)(dw4, reinterpret_cast<float*>(out), rows_kt, g->Cin);
     MCG_CHECK_LAUNCH(who);
     return 0;
   }

@@ -18,3 +18,9 @@ for r in rows:
     print("%-8s %-14s %.4f ms x%d  %6.0f TF/s  %.2f" % (r["layer"], r["kernel"], r["ms"], r["calls_per_step"], r["tflops"],
                                                       r["frac_of_burst_peak"]))
 print("sum over step: %.3f ms; tc error flag %d" % (tot, K.tc_error_flag()))
+ntot = 0.0
+for r in bench.time_narrow_layers(K, torch, peaks):
+    ntot += r["ms"] * r["calls_per_step"]
+    print("%-8s %-40s %.4f ms x%d  %6.0f GB/s  %.2f" % (r["layer"], r["kernel"], r["ms"], r["calls_per_step"], r["gb_per_s"],
+                                                      r["frac_of_hbm_peak"]))
+print("3-channel layers, sum over step: %.3f ms" % ntot)
