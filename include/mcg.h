@@ -162,6 +162,9 @@ int mcg_loss_gen(const float* y_i, const float* y_v, const int* t_fake, int N, i
 int mcg_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float alpha, float beta1,
                   float beta2, float eps, float wd, float grad_scale, const int* t_ptr, void* stream);
 int mcg_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+/* The inverse (n % 8 == 0, 16-byte aligned): the data-parallel layer sends a model's flat gradient through the
+ * all-reduce as bf16 (half the NVLink bytes) and widens the sum back into the fp32 gradient buffer Adam reads.    */
+int mcg_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream);
 /* Link.cleargrads (Chainer: optimizer.update -> target.cleargrads, updater.py:111-113): the flat gradient buffer of a
  * model is zero-filled on the stream (cudaMemsetAsync: a memset node in a captured step, no kernel).           */
 int mcg_fill_zero(void* p, size_t bytes, void* stream);

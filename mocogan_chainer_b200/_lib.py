@@ -51,6 +51,7 @@ SIGNATURES = {
     "mcg_loss_gen": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "mcg_adam_step": (_i, [_p, _p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _f, _p, _p]),
     "mcg_cast_f32_to_bf16": (_i, [_p, _p, _ll, _p]),
+    "mcg_cast_bf16_to_f32": (_i, [_p, _p, _ll, _p]),
     "mcg_fill_zero": (_i, [_p, _sz, _p]),
     "mcg_pad_channels": (_i, [_p, _p, _ll, _i, _i, _i, _p]),
     "mcg_step_state_init": (_i, [_p, C.c_ulonglong, _p]),

@@ -606,6 +606,28 @@ __global__ void cast_kernel(const float* __restrict__ s, __nv_bfloat16* __restri
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     d[i] = __float2bfloat16_rn(s[i]);
 }
+// 8 elements per thread (n % 8 == 0, 16-byte aligned): the gradient arenas on their way into / out of the bf16 all-reduce
+__global__ void __launch_bounds__(256) cast8_f32_bf16_kernel(const float4* __restrict__ s, uint4* __restrict__ d, long long n8) {
+  pdl_enter();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = s[2 * i], b = s[2 * i + 1];
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+    h[0] = __floats2bfloat162_rn(a.x, a.y); h[1] = __floats2bfloat162_rn(a.z, a.w);
+    h[2] = __floats2bfloat162_rn(b.x, b.y); h[3] = __floats2bfloat162_rn(b.z, b.w);
+    d[i] = u;
+  }
+}
+__global__ void __launch_bounds__(256) cast8_bf16_f32_kernel(const uint4* __restrict__ s, float4* __restrict__ d, long long n8) {
+  pdl_enter();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = s[i];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]), c = __bfloat1622float2(h[2]), e = __bfloat1622float2(h[3]);
+    d[2 * i] = make_float4(a.x, a.y, b.x, b.y);
+    d[2 * i + 1] = make_float4(c.x, c.y, e.x, e.y);
+  }
+}
 __global__ void state_init_kernel(StepState* s, unsigned long long seed) {
   pdl_enter();
   s->seed_lo = (uint32_t)seed; s->seed_hi = (uint32_t)(seed >> 32);
@@ -895,8 +917,19 @@ int mcg_pad_channels(const void* src, void* dst, long long rows, int C, int Cp, 
 
 int mcg_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
   if (!src || !dst || n <= 0) MCG_FAIL(MCG_ERR_SHAPE, "mcg_cast_f32_to_bf16: bad arguments");
-  pdl(cast_kernel, grid_for(n), 256, 0, as_stream(stream))(src, (__nv_bfloat16*)dst, n);
+  if (n % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0)
+    pdl(cast8_f32_bf16_kernel, grid_for(n / 8), 256, 0, as_stream(stream))((const float4*)src, (uint4*)dst, n / 8);
+  else
+    pdl(cast_kernel, grid_for(n), 256, 0, as_stream(stream))(src, (__nv_bfloat16*)dst, n);
   MCG_CHECK_LAUNCH("mcg_cast_f32_to_bf16");
+  return 0;
+}
+
+int mcg_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream) {
+  if (!src || !dst || n <= 0 || n % 8 || (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
+    MCG_FAIL(MCG_ERR_SHAPE, "mcg_cast_bf16_to_f32: needs n %% 8 == 0 and 16-byte aligned buffers");
+  pdl(cast8_bf16_f32_kernel, grid_for(n / 8), 256, 0, as_stream(stream))((const uint4*)src, (float4*)dst, n / 8);
+  MCG_CHECK_LAUNCH("mcg_cast_bf16_to_f32");
   return 0;
 }
 

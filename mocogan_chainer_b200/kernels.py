@@ -232,6 +232,10 @@ def cast_bf16(src, dst):
     check(lib().mcg_cast_f32_to_bf16(ptr(src), ptr(dst), src.numel(), stream()), "mcg_cast_f32_to_bf16")
 
 
+def cast_f32(src, dst):
+    check(lib().mcg_cast_bf16_to_f32(ptr(src), ptr(dst), src.numel(), stream()), "mcg_cast_bf16_to_f32")
+
+
 def step_state_new(seed, device):
     st = torch.zeros(8, dtype=torch.int32, device=device)
     check(lib().mcg_step_state_init(ptr(st), int(seed) & (2 ** 64 - 1), stream()), "mcg_step_state_init")

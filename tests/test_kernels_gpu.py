@@ -475,3 +475,26 @@ def test_adam_weight_decay_three_steps(K):
     torch.cuda.synchronize()
     assert np.abs(pd.cpu().numpy() - params["w"]).max() < 2e-6
     assert torch.equal(pb, pd.bfloat16())
+
+
+def test_cast_round_trip_and_helpers(K):
+    """mcg_cast_f32_to_bf16 (vector and scalar path) / mcg_cast_bf16_to_f32 (the bf16 gradient all-reduce's two passes),
+    mcg_fill_zero, mcg_pad_channels — bit-exact against torch's conversions."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for n in (8 * 1001, 1003):
+        a = torch.randn(n, device="cuda", generator=g) * 3
+        b = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+        K.cast_bf16(a, b)
+        assert torch.equal(b, a.bfloat16())
+        if n % 8 == 0:
+            c = torch.empty(n, device="cuda")
+            K.cast_f32(b, c)
+            assert torch.equal(c, b.float())
+    z = torch.ones(4097, device="cuda")
+    K.fill_zero(z)
+    src = torch.randn((70, 1, 1, 1, 60), device="cuda", generator=g).bfloat16()
+    dst = torch.full((70, 1, 1, 1, 64), 7.0, dtype=torch.bfloat16, device="cuda")
+    K.pad_channels(src, dst)
+    torch.cuda.synchronize()
+    assert float(z.abs().max()) == 0.0
+    assert torch.equal(dst[..., :60], src) and float(dst[..., 60:].abs().max()) == 0.0
