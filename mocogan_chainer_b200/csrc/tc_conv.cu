@@ -72,6 +72,11 @@ struct TcParams {
   int box_tn;   // 1: boxes are numbered (w, h, n, t) — frames slowest — so the MT boxes of a step share their frame and skip alike
   int debug_skip_epi;
   int out_f32, ocols;                                        // ocols = channels of one output pixel row
+  // depth-to-space epilogue (merged-class data gradient of the 3-channel layers): column ((e*sH + a)*sW + b)*C + ci of cell
+  // (l, i, j) is input pixel (l*sT + e, i*sH + a, j*sW + b), channel ci; d2s_C = C (0 = off), d2s_* = the input tensor's extents
+  int d2s_C, d2s_sT, d2s_sH, d2s_sW, d2s_Ti, d2s_Hi, d2s_Wi, d2s_cols;
+  uint32_t d2s_tab[32];   // per column: e | a << 4 | b << 8 | ci << 12 (read with compile-time indices: the accumulators stay in registers)
+  int store_cols;   // > 0 (bf16 row-major output): only the first store_cols columns (a multiple of 8) of a row are written, rows are store_cols wide
   int planar_chunk, planar_cols;   // fprop: write column c to plane c/chunk as [plane][pixel][chunk] (0 = row-major)
   long long planar_stride;
   uint8_t planar_plane[64], planar_within[64];   // per 4-column group c/4: plane index and offset inside the plane's chunk
@@ -287,10 +292,30 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& P, void* __rest
               for (int i = 0; i < 32; ++i) v[i] = 0u;
             }
             float f[32];
+            const bool colbias = bias && !(MODE == kFprop && P.d2s_C);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + (bias ? bias[ncol0 + c0 + i] : 0.f);
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + (colbias ? bias[ncol0 + c0 + i] : 0.f);
             if (valid) {
-              if (MODE == kFprop && P.planar_chunk) {
+              if (MODE == kFprop && P.d2s_C) {
+                // the cell's sT*sH*sW*C values go straight to their pixels of dx (no Zm matrix, no depth-to-space pass);
+                // all of them sit in the first 32 columns, so only the half-0 warps store
+                if (c0 == 0) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    if (i < P.d2s_cols) {
+                      const uint32_t tb = P.d2s_tab[i];
+                      const int ti = ot * P.d2s_sT + (int)(tb & 15), hi = oh * P.d2s_sH + (int)((tb >> 4) & 15);
+                      const int wi = ow * P.d2s_sW + (int)((tb >> 8) & 15), ci = (int)(tb >> 12);
+                      if (ti < P.d2s_Ti && hi < P.d2s_Hi && wi < P.d2s_Wi) {
+                        const long long dst = ((((long long)on * P.d2s_Ti + ti) * P.d2s_Hi + hi) * P.d2s_Wi + wi) * P.d2s_C + ci;
+                        const float val = f[i] + (bias ? bias[ci] : 0.f);
+                        if (P.out_f32) reinterpret_cast<float*>(out)[dst] = val;
+                        else reinterpret_cast<__nv_bfloat16*>(out)[dst] = __float2bfloat16_rn(val);
+                      }
+                    }
+                  }
+                }
+              } else if (MODE == kFprop && P.planar_chunk) {
                 // planar bf16 output for the narrow-Cin dgrad GEMM: plane = (kt,kh) run, so col2im reads contiguous lines
                 __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
 #pragma unroll
@@ -311,8 +336,10 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& P, void* __rest
                 for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
               } else {
                 __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + base + c0;
+                const int lim = P.store_cols ? P.store_cols - (ncol0 + c0) : 32;   // columns beyond store_cols are not written
 #pragma unroll
                 for (int i = 0; i < 32; i += 8) {
+                  if (i >= lim) break;
                   uint4 u;
                   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
                   h[0] = __floats2bfloat162_rn(f[i], f[i + 1]);
@@ -1538,7 +1565,8 @@ bool tc_supported(const mcg_conv_geom* g) {
 }
 
 int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void* out, const float* bias, int out_dtype,
-            cudaStream_t st, int kreal = 0, int planar_chunk = 0, int planar_cols = 0, int wrows = 0, const TcWin* win = nullptr) {
+            cudaStream_t st, int kreal = 0, int planar_chunk = 0, int planar_cols = 0, int wrows = 0, const TcWin* win = nullptr,
+            const int* d2s = nullptr, int store_cols = 0) {   // d2s: {C, sT, sH, sW, Ti, Hi, Wi} -> depth-to-space epilogue (fprop)
   const char* who = mode == kFprop ? "mcg_conv_fprop(tc)" : mode == kDgrad ? "mcg_conv_dgrad(tc)" : "mcg_conv_wgrad(tc)";
   if (!tc_supported(g)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: needs Cin,Cout %% 64 == 0, stride <= 2, <= 64 taps", who);
   TcParams P;
@@ -1548,6 +1576,15 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
   P.out_f32 = (out_dtype == MCG_F32);
   P.planar_chunk = planar_chunk;
   P.planar_cols = planar_cols;
+  if (d2s) {
+    if (mode != kFprop || d2s[0] * d2s[1] * d2s[2] * d2s[3] > 32) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: depth-to-space epilogue", who);
+    P.d2s_C = d2s[0]; P.d2s_sT = d2s[1]; P.d2s_sH = d2s[2]; P.d2s_sW = d2s[3]; P.d2s_Ti = d2s[4]; P.d2s_Hi = d2s[5]; P.d2s_Wi = d2s[6];
+    P.d2s_cols = d2s[0] * d2s[1] * d2s[2] * d2s[3];
+    for (int e = 0, c = 0; e < d2s[1]; ++e)
+      for (int a2 = 0; a2 < d2s[2]; ++a2)
+        for (int b2 = 0; b2 < d2s[3]; ++b2)
+          for (int ci = 0; ci < d2s[0]; ++ci, ++c) P.d2s_tab[c] = (uint32_t)(e | (a2 << 4) | (b2 << 8) | (ci << 12));
+  }
   P.planar_stride = (long long)g->Wo * planar_chunk;   // planar mode is only used on 1-D line geometries (M = Wo)
   // wrows < Cout: the weight tensor has fewer rows than the (zero-padded) channel count of the activations it meets —
   // rows beyond are TMA out-of-bounds zero fill, columns of dw beyond are not written
@@ -1577,6 +1614,11 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
     P.cls_w = P.cls_h = P.cls_t = 1;
     P.os_w = g->Cout; P.os_h = (long long)g->Wo * g->Cout; P.os_t = (long long)g->Ho * P.os_h; P.os_n = (long long)g->To * P.os_t;
     P.ocols = g->Cout;
+    if (store_cols > 0) {       // narrow row-major output: rows of store_cols (< Cout) columns
+      if (store_cols % 8 || store_cols > g->Cout || out_dtype != MCG_BF16) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: store_cols %d", who, store_cols);
+      P.store_cols = store_cols;
+      P.os_w = store_cols; P.os_h = (long long)g->Wo * store_cols; P.os_t = (long long)g->Ho * P.os_h; P.os_n = (long long)g->To * P.os_t;
+    }
     P.chunks = g->Cin / 64;
     P.tap_begin[0] = 0; P.tap_count[0] = taps;
     for (int kt = 0, j = 0; kt < g->kT; ++kt)
@@ -1972,7 +2014,7 @@ __global__ void merged_weights_kernel(const __nv_bfloat16* __restrict__ w, __nv_
 // (sW neighbouring pixels of one line), so the thread moves one short contiguous run.
 __global__ void __launch_bounds__(256) depth_to_space_kernel(const __nv_bfloat16* __restrict__ zm, const float* __restrict__ bias,
                                                              void* __restrict__ dx, int out_f32, long long cells, int Cin, int Ti,
-                                                             int Hi, int Wi, int L, int I, int J, int sT, int sH, int sW) {
+                                                             int Hi, int Wi, int L, int I, int J, int sT, int sH, int sW, int zcols) {
   pdl_enter();
   const int RUN = sW * Cin, sub = sT * sH;
   const long long total = cells * sub;
@@ -1986,7 +2028,7 @@ __global__ void __launch_bounds__(256) depth_to_space_kernel(const __nv_bfloat16
     const int e = ea / sH, a = ea % sH;
     const int ti = l * sT + e, hi = i * sH + a, wi0 = j * sW;
     if (ti >= Ti || hi >= Hi) continue;
-    const __nv_bfloat16* src = zm + (idx / sub) * 64 + ea * RUN;
+    const __nv_bfloat16* src = zm + (idx / sub) * zcols + ea * RUN;
     const long long dst = (((n * Ti + ti) * Hi + hi) * (long long)Wi + wi0) * Cin;
     for (int q = 0; q < RUN; ++q) {
       if (wi0 + q / Cin >= Wi) break;
@@ -2123,11 +2165,20 @@ int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b
       MCG_CHECK_LAUNCH(who);
       // stride-1 fprop over dy: "input" = dy, window (nT,nH,nW), zero padding -dmin (the far side is TMA out-of-bounds fill)
       mcg_conv_geom g2 = {g->N, g->Cout, 64, g->To, g->Ho, g->Wo, L, I, J, G.nT, G.nH, G.nW, 1, 1, 1, -G.dt_min, -G.dh_min, -G.dw_min};
-      if ((rc = tc_conv(kFprop, &g2, a, wm, zm, nullptr, MCG_BF16, st))) return rc;
+      if (g->sT * g->sH * g->sW * g->Cin <= 32 && G.nT * G.nH * G.nW >= 18 && !tc_env_int("MCG_TC_NOD2S")) {
+        // the convolution's epilogue writes every cell's values straight to their pixels of dx (+ bias): no Zm, no extra
+        // pass.  Only where the K loop is long enough to hide the scattered 2-byte stores (Dv.dc1: 36 taps, 0.189 ->
+        // 0.171 ms); the 2-D layers' 9-tap loop is epilogue-bound already (G.dc5: 0.101 -> 0.119 ms with it)
+        const int d2s[7] = {g->Cin, g->sT, g->sH, g->sW, g->Ti, g->Hi, g->Wi};
+        return tc_conv(kFprop, &g2, a, wm, out, bias, out_dtype, st, 0, 0, 0, 0, nullptr, d2s);
+      }
+      // Zm keeps only the columns that carry classes (rounded up to 8): 32 B instead of 128 B per cell for the 2-D layers
+      const int zcols = (int)round_up((long long)g->sT * g->sH * g->sW * g->Cin, 8);
+      if ((rc = tc_conv(kFprop, &g2, a, wm, zm, nullptr, MCG_BF16, st, 0, 0, 0, 0, nullptr, nullptr, zcols))) return rc;
       long long nb = (cells * g->sT * g->sH + 255) / 256;
       if (nb > (long long)num_sms() * 16) nb = (long long)num_sms() * 16;
       pdl(depth_to_space_kernel, (unsigned)nb, 256, 0, st)(zm, bias, out, out_dtype == MCG_F32, cells, g->Cin, g->Ti, g->Hi, g->Wi,
-                                                         L, I, J, g->sT, g->sH, g->sW);
+                                                         L, I, J, g->sT, g->sH, g->sW, zcols);
       MCG_CHECK_LAUNCH(who);
       return 0;
     }
