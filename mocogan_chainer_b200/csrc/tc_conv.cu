@@ -2084,6 +2084,77 @@ __global__ void __launch_bounds__(256) interleave_rows_kernel(const __nv_bfloat1
     xk[2 * i + 1] = *reinterpret_cast<const uint4*>(v + 8);
   }
 }
+// The same, one block per (frame, ho): the kH = 4 source rows are staged in shared memory with 16-byte loads (a row of
+// the channels-last image is contiguous), then every thread assembles whole 32-byte output pixels.  W*C % 8 == 0.
+__global__ void __launch_bounds__(128) interleave_rows_line_kernel(const __nv_bfloat16* __restrict__ x, uint4* __restrict__ xk, int H,
+                                                                   int W, int C, int Ho, int Wq, int sH, int pH, int pW) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned short srow[];     // [4][W*C]
+  const int RW = W * C, vpr = RW / 8;
+  const int ho = blockIdx.x % Ho;
+  const long long f = blockIdx.x / Ho;
+  uint4* s128 = reinterpret_cast<uint4*>(srow);
+  for (int e = threadIdx.x; e < 4 * vpr; e += blockDim.x) {
+    const int kh = e / vpr, j = e - kh * vpr;
+    const int h = ho * sH + kh - pH;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if ((unsigned)h < (unsigned)H) v = __ldg(reinterpret_cast<const uint4*>(x + (f * H + h) * (long long)RW) + j);
+    s128[e] = v;
+  }
+  __syncthreads();
+  uint4* dst = xk + ((f * Ho + ho) * (long long)Wq) * 2;
+  for (int wq = threadIdx.x; wq < Wq; wq += blockDim.x) {
+    const int w = wq - pW;
+    __align__(16) unsigned short v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 0;
+    if ((unsigned)w < (unsigned)W) {
+#pragma unroll
+      for (int kh = 0; kh < 4; ++kh)
+        for (int c = 0; c < C; ++c) v[kh * 4 + c] = srow[kh * RW + w * C + c];
+    }
+    dst[2 * wq] = *reinterpret_cast<const uint4*>(v);
+    dst[2 * wq + 1] = *reinterpret_cast<const uint4*>(v + 8);
+  }
+}
+// Patch rows: xp[f][ho][wo][kw][kh][c4] = x[f][ho*sH + kh - pH][wo*sW + kw - pW][c] — the 4 x 4 spatial window of every
+// OUTPUT pixel as one 128-byte row (a 2-D im2col per frame: 73 MB for Dv.dc1 against 179 MB for the full 3-D im2col; the
+// temporal taps stay implicit).  The rows are 128-byte aligned, which the overlapping window view's are not (its rows
+// start every 64 B) — an alternative to the window view, opt-in (MCG_TC_PATCHROWS=1): measured slower.
+// One block per (frame, ho); W*C % 8 == 0.
+__global__ void __launch_bounds__(128) patch_rows_line_kernel(const __nv_bfloat16* __restrict__ x, uint4* __restrict__ xp, int H, int W,
+                                                              int C, int Ho, int Wo, int sH, int sW, int pH, int pW) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned short srow[];     // [4][W*C]
+  const int RW = W * C, vpr = RW / 8;
+  const int ho = blockIdx.x % Ho;
+  const long long f = blockIdx.x / Ho;
+  uint4* s128 = reinterpret_cast<uint4*>(srow);
+  for (int e = threadIdx.x; e < 4 * vpr; e += blockDim.x) {
+    const int kh = e / vpr, j = e - kh * vpr;
+    const int h = ho * sH + kh - pH;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if ((unsigned)h < (unsigned)H) v = __ldg(reinterpret_cast<const uint4*>(x + (f * H + h) * (long long)RW) + j);
+    s128[e] = v;
+  }
+  __syncthreads();
+  // a thread writes one (wo, kw) quarter row = 32 B = [kh][c4]; consecutive threads write consecutive 32-byte pieces
+  uint4* dst = xp + ((f * Ho + ho) * (long long)Wo) * 8;
+  for (int i = threadIdx.x; i < Wo * 4; i += blockDim.x) {
+    const int wo = i >> 2, kw = i & 3;
+    const int w = wo * sW + kw - pW;
+    __align__(16) unsigned short v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 0;
+    if ((unsigned)w < (unsigned)W) {
+#pragma unroll
+      for (int kh = 0; kh < 4; ++kh)
+        for (int c = 0; c < C; ++c) v[kh * 4 + c] = srow[kh * RW + w * C + c];
+    }
+    dst[2 * i] = *reinterpret_cast<const uint4*>(v);
+    dst[2 * i + 1] = *reinterpret_cast<const uint4*>(v + 8);
+  }
+}
 // w4[co][kt][kw][kh][0..4) = w[co][kt][kh][kw][c < C], 0 beyond: the K order of the window rows
 __global__ void pad_w4_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ w4, int rows_kt, int C) {
   pdl_enter();
@@ -2109,7 +2180,8 @@ struct WinLayout { int Wq; size_t xq_bytes, w4_bytes, dw4_bytes; };
 static WinLayout win_layout(const mcg_conv_geom* g) {
   WinLayout L;
   L.Wq = g->Wi + g->pW > (g->Wo - 1) * g->sW + g->kW ? g->Wi + g->pW : (g->Wo - 1) * g->sW + g->kW;
-  L.xq_bytes = (size_t)round_up((long long)g->N * g->Ti * g->Ho * L.Wq * 32, 1024);
+  const long long win_b = (long long)g->N * g->Ti * g->Ho * L.Wq * 32, patch_b = (long long)g->N * g->Ti * g->Ho * g->Wo * 128;
+  L.xq_bytes = (size_t)round_up(win_b > patch_b ? win_b : patch_b, 1024);
   L.w4_bytes = (size_t)round_up((long long)g->Cout * g->kT * 64 * 2, 1024);
   L.dw4_bytes = (size_t)round_up((long long)g->Cout * g->kT * 64 * 4, 1024);
   return L;
@@ -2206,16 +2278,45 @@ int tc_conv_small(int mode, const mcg_conv_geom* g, const void* a, const void* b
     float* dw4 = reinterpret_cast<float*>(base + L.xq_bytes + L.w4_bytes);
     const long long frames = (long long)g->N * g->Ti;
     if (frames * g->Ho > 0x7fffffffLL) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: too many rows", who);
+    const int rows_kt = g->Cout * g->kT, rows_taps = rows_kt * 16;
+    // default: the row-interleaved copy read through the overlapping window view.  MCG_TC_PATCHROWS=1: patch rows (one
+    // 128-byte aligned row per output pixel, twice the bytes) through an ordinary activation map — measured slower
+    // (Dv.dc1 fprop 0.089 against 0.073 ms), kept as the A/B that showed the window rows' 64-byte alignment is not a cost
+    const bool patches = tc_env_int("MCG_TC_PATCHROWS") && (g->Wi * g->Cin) % 8 == 0 && (size_t)g->Wi * g->Cin * 8 <= 48 * 1024;
+    if (patches) {
+      if (!cols_valid) {
+        pdl(patch_rows_line_kernel, (unsigned)(frames * g->Ho), 128, (size_t)g->Wi * g->Cin * 8, st)(
+            (const __nv_bfloat16*)a, reinterpret_cast<uint4*>(xq), g->Hi, g->Wi, g->Cin, g->Ho, g->Wo, g->sH, g->sW, g->pH, g->pW);
+        MCG_CHECK_LAUNCH(who);
+      }
+      // xp is a plain channels-last tensor (N, Ti, Ho, Wo, 64): a kT x 1 x 1 convolution over it
+      mcg_conv_geom gp = {g->N, 64, g->Cout, g->Ti, g->Ho, g->Wo, g->To, g->Ho, g->Wo, g->kT, 1, 1, 1, 1, 1, 0, 0, 0};
+      if (mode == kFprop) {
+        pdl(pad_w4_kernel, 32, 256, 0, st)((const __nv_bfloat16*)b, w4, rows_kt, g->Cin);
+        MCG_CHECK_LAUNCH(who);
+        return tc_conv(kFprop, &gp, xq, w4, out, bias, out_dtype, st);
+      }
+      cudaError_t e = cudaMemsetAsync(dw4, 0, (size_t)rows_taps * 4 * sizeof(float), st);
+      if (e != cudaSuccess) MCG_FAIL((int)e, "%s: cudaMemsetAsync: %s", who, cudaGetErrorString(e));
+      if ((rc = tc_conv(kWgrad, &gp, xq, b, dw4, nullptr, MCG_F32, st))) return rc;
+      pdl(unpad_dw4_kernel, 32, 256, 0, st)(dw4, reinterpret_cast<float*>(out), rows_kt, g->Cin);
+      MCG_CHECK_LAUNCH(who);
+      return 0;
+    }
     if (!cols_valid) {
+      if ((g->Wi * g->Cin) % 8 == 0 && frames * g->Ho < 0x7fffffffLL && (size_t)g->Wi * g->Cin * 8 <= 48 * 1024) {
+        pdl(interleave_rows_line_kernel, (unsigned)(frames * g->Ho), 128, (size_t)g->Wi * g->Cin * 8, st)(
+            (const __nv_bfloat16*)a, reinterpret_cast<uint4*>(xq), g->Hi, g->Wi, g->Cin, g->Ho, L.Wq, g->sH, g->pH, g->pW);
+      } else {
       long long nb = (frames * g->Ho * L.Wq + 255) / 256;
       if (nb > (long long)num_sms() * 16) nb = (long long)num_sms() * 16;
       pdl(interleave_rows_kernel, (unsigned)nb, 256, 0, st)((const __nv_bfloat16*)a, reinterpret_cast<uint4*>(xq), frames, g->Hi,
                                                             g->Wi, g->Cin, g->Ho, L.Wq, g->sH, g->pH, g->pW);
+      }
       MCG_CHECK_LAUNCH(who);
     }
     const TcWin win{xq, L.Wq, g->Ho, g->Wo, (int)frames, g->Ti, g->sW};
     mcg_conv_geom g2 = {g->N, 64, g->Cout, g->Ti, g->Ho, g->Wo, g->To, g->Ho, g->Wo, g->kT, 1, 1, 1, 1, 1, 0, 0, 0};
-    const int rows_kt = g->Cout * g->kT, rows_taps = rows_kt * 16;
     if (mode == kFprop) {
       pdl(pad_w4_kernel, 32, 256, 0, st)((const __nv_bfloat16*)b, w4, rows_kt, g->Cin);
       MCG_CHECK_LAUNCH(who);

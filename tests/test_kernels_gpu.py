@@ -134,6 +134,7 @@ TC_CASES = [
     ("tc_di_dc1", 2, 3, 3, 64, (16, 16), (4, 4), (2, 2), (1, 1)),
     ("tc_dv_dc1", 3, 2, 3, 64, (7, 16, 16), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
     ("tc_c1", 2, 3, 1, 64, (16, 16), (4, 4), (2, 2), (1, 1)),
+    ("tc_di_odd", 2, 3, 3, 64, (10, 10), (4, 4), (2, 2), (1, 1)),     # W*C % 8 != 0: the scalar row-interleave pass
     # class-fused data gradient (Cin = 64, k4 s2 p1, >= 2 x 148 pixel blocks): 315 blocks = pairs + 19 blocks dealt out as
     # single-class units, temporal taps skipped at both ends of the clip; 460 blocks = odd per-CTA count (pair + single)
     ("tc3d_fused", 3, 10, 64, 64, (7, 48, 48), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
