@@ -238,6 +238,30 @@ __device__ __forceinline__ TcBox tc_decode_box(const TcParams& P, int bi) {
   return b;
 }
 
+// The boxes of one step are consecutive: the first is decoded with divisions, the others follow by carrying.  (The
+// epilogue of the short-K launches — the 3-channel layers' GEMMs, the generator's 2-D layers — decoded every box from
+// scratch, with the divisors re-read from the parameter bank each time: ~3,500 cycles per 128-row block against ~500 of
+// actual work, ncu source page of Dv.dc1's fprop.)
+struct TcBoxDims {
+  int BW, BH, BT, BB, wl, hl, tl, nl, tn;
+  __device__ __forceinline__ explicit TcBoxDims(const TcParams& P)
+      : BW(P.BW), BH(P.BH), BT(P.BT), BB(P.BB), wl(P.nbw * P.BW), hl(P.nbh * P.BH), tl(P.nbt * P.BT), nl(P.nbb * P.BB), tn(P.box_tn) {}
+  __device__ __forceinline__ void next(TcBox& b) const {
+    b.w0 += BW;
+    if (b.w0 < wl) return;
+    b.w0 = 0; b.h0 += BH;
+    if (b.h0 < hl) return;
+    b.h0 = 0;
+    if (tn) {
+      b.n0 += BB;
+      if (b.n0 >= nl) { b.n0 = 0; b.t0 += BT; }
+    } else {
+      b.t0 += BT;
+      if (b.t0 >= tl) { b.t0 = 0; b.n0 += BB; }
+    }
+  }
+};
+
 // Epilogue role (warps 2-9), shared by the kernels below: walks the same segment sequence as the producer / MMA roles,
 // waits for an accumulator buffer, moves TMEM -> registers -> global, and hands the buffer back.
 // A lone warp per scheduler runs the epilogue's dependent instruction chains at a fraction of the issue rate, so two
@@ -254,6 +278,18 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& P, void* __rest
     uint32_t seg = 0;
     long long ru, ru_end;
     bool alive = true;
+    // per-thread constants of the fprop / dgrad epilogue: this row's pixel inside a box, the box walker, output geometry
+    const TcBoxDims bd(P);
+    int e_iw = 0, e_ih = 0, e_it = 0, e_ib = 0;
+    if (MODE != kWgrad) {
+      int rr = r;
+      e_iw = rr % P.BW; rr /= P.BW;
+      e_ih = rr % P.BH; rr /= P.BH;
+      e_it = rr % P.BT; rr /= P.BT;
+      e_ib = rr;
+    }
+    const int e_mw = P.o_mul_w, e_mh = P.o_mul_h, e_mt = P.o_mul_t, e_fw = P.full_w, e_fh = P.full_h, e_ft = P.full_t, e_en = P.EN;
+    const long long e_sn = P.os_n, e_st = P.os_t, e_sh = P.os_h, e_sw = P.os_w;
     while (alive && rng.next(P, ru, ru_end, err)) {
     iter.set(ru, ru_end);
     while (iter.next(P, sg)) {
@@ -269,18 +305,15 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& P, void* __rest
       if (MODE != kWgrad) {
         const int cls = mg;
         const int pw = cls % P.cls_w, phh = (cls / P.cls_w) % P.cls_h, pt = cls / (P.cls_w * P.cls_h);
-        int rr = r;
-        const int iw = rr % P.BW; rr /= P.BW;
-        const int ih = rr % P.BH; rr /= P.BH;
-        const int itt = rr % P.BT; rr /= P.BT;
-        const int ib = rr;
+        const int iw = e_iw, ih = e_ih, itt = e_it, ib = e_ib;
+        TcBox bx = tc_decode_box(P, sg.box0);
 #pragma unroll 1
         for (int m = 0; m < sg.nlive; ++m) {
-          const TcBox bx = tc_decode_box(P, sg.box0 + m);
-          const int ow = (bx.w0 + iw) * P.o_mul_w + pw, oh = (bx.h0 + ih) * P.o_mul_h + phh, ot = (bx.t0 + itt) * P.o_mul_t + pt;
+          if (m) bd.next(bx);
+          const int ow = (bx.w0 + iw) * e_mw + pw, oh = (bx.h0 + ih) * e_mh + phh, ot = (bx.t0 + itt) * e_mt + pt;
           const int on = bx.n0 + ib;
-          const bool valid = ow < P.full_w && oh < P.full_h && ot < P.full_t && on < P.EN;
-          const long long base = (long long)on * P.os_n + (long long)ot * P.os_t + (long long)oh * P.os_h + (long long)ow * P.os_w + ncol0;
+          const bool valid = ow < e_fw && oh < e_fh && ot < e_ft && on < e_en;
+          const long long base = (long long)on * e_sn + (long long)ot * e_st + (long long)oh * e_sh + (long long)ow * e_sw + ncol0;
 #pragma unroll 1
           for (int c0 = half * 32; c0 < BN; c0 += 64) {
             uint32_t v[32];
@@ -445,6 +478,7 @@ __global__ void __launch_bounds__(kTcConvThreads, 1) tc_conv_kernel(const __grid
       TcSegIter<MODE, MT> iter;
       TcSeg sg;
       uint32_t kstep = 0;   // ring steps issued by either producer so far
+      const TcBoxDims pbd(P);
       int s = 0;
       uint32_t ph = 1;   // ring slot and the parity its `empty` barrier is waited with
       uint32_t stage_a = smem_a, full_s = full_a, empty_s = empty_a;
@@ -495,12 +529,16 @@ __global__ void __launch_bounds__(kTcConvThreads, 1) tc_conv_kernel(const __grid
         if (MODE != kWgrad) {
           const int cls = mg;
           TcBox bx[MT];
+          {
+            TcBox cur = tc_decode_box(P, sg.box0);
 #pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            bx[m] = tc_decode_box(P, sg.box0 + (m < sg.nlive ? m : 0));
-            bx[m].w0 = bx[m].w0 * P.a_mul_w + P.a_add_w;
-            bx[m].h0 = bx[m].h0 * P.a_mul_h + P.a_add_h;
-            bx[m].t0 = bx[m].t0 * P.a_mul_t + P.a_add_t;
+            for (int m = 0; m < MT; ++m) {
+              if (m && m < sg.nlive) pbd.next(cur);
+              bx[m].w0 = cur.w0 * P.a_mul_w + P.a_add_w;
+              bx[m].h0 = cur.h0 * P.a_mul_h + P.a_add_h;
+              bx[m].t0 = cur.t0 * P.a_mul_t + P.a_add_t;
+              bx[m].n0 = cur.n0;
+            }
           }
           const uint32_t tx_bytes = sg.nlive * A_BYTES + B_BYTES;
           const int chunks = P.chunks;
