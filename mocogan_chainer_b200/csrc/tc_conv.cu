@@ -1279,7 +1279,12 @@ __device__ __forceinline__ TcBox tc4_decode_box(const Tc4Params& P, int bi) {
   return b;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) tc_dgrad4_kernel(const __grid_constant__ CUtensorMap mapA,
+// 352 threads: warp 0 producer, warps 1 and 10 MMA issuers (one per pixel block of the pair), warps 2-9 epilogue.  With one
+// issuer the kernel was bound by that thread's instruction stream even after the stage table became compile-time (ncu
+// source page: 399 of its 444 samples issuing, 45 waiting for data, ~115 cycles per MMA against ~50 of tensor time): the two
+// blocks of a pair accumulate into disjoint TMEM columns from the same weight slabs, so each gets its own issuing thread.
+constexpr int kT4Threads = 352;
+__global__ void __launch_bounds__(kT4Threads, 1) tc_dgrad4_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                   const __grid_constant__ CUtensorMap mapB,
                                                                   const __grid_constant__ Tc4Params P, void* __restrict__ out,
                                                                   const float* __restrict__ bias) {
@@ -1292,8 +1297,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dgrad4_kernel(const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* err = &g_tc_error;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kT4Bars; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(&tfull_bar, 1);
+    for (int i = 0; i < kT4Bars; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 2); }   // both issuers release a stage
+    mbar_init(&tfull_bar, 2);
     mbar_init(&tempty_bar, kEpiThreads);
     fence_barrier_init();
     tma_prefetch_desc(&mapA);
@@ -1357,8 +1362,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dgrad4_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 10) {
     if (elect_one()) {
+      // issuer `mine` owns block `mine` of every pair.  Both walk every stage (and wait for its data, which keeps them
+      // within one ring of each other); a stage is released by two arrivals — a tcgen05.commit from an issuer that
+      // multiplied from it, a plain arrive from one that had no block in it (single-block steps).
+      const int mine = warp == 1 ? 0 : 1;
       const uint32_t desc_hi = smem_desc_hi(1024);
       const uint32_t id64 = make_idesc_bf16(128, 64, 0, 1), id128 = make_idesc_bf16(128, 128, 0, 1), id256 = make_idesc_bf16(128, 256, 0, 1);
       Tc4Iter iter(P);
@@ -1371,6 +1380,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dgrad4_kernel(const __grid_c
         if (!mbar_wait_a(tempty_a, (nseg & 1) ^ 1, err)) break;
         tc_fence_after();
         const int steps = sg.kt_n * P.chunks;
+        const bool active = mine < sg.nlive;
         bool first = true;
         for (int g = 0; alive && g < steps; ++g) {
 #pragma unroll
@@ -1382,24 +1392,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dgrad4_kernel(const __grid_c
             const int bar = istage % kT4Bars;
             if (!mbar_wait_a(full_a + bar * 8, (istage / kT4Bars) & 1, err)) { alive = false; break; }
             ++istage;
-            tc_fence_after();
-            for (int m = 0; m < sg.nlive; ++m) {
-              const uint32_t a_lo = smem_desc_lo(smem_a + (m ? a1 : a0) * kT4Gran, 16);
+            if (active) {
+              tc_fence_after();
+              const uint32_t a_lo = smem_desc_lo(smem_a + (mine ? a1 : a0) * kT4Gran, 16);
 #pragma unroll
               for (int j = 0; j < T[s].nmma; ++j) {
-                const uint32_t d = tmem + m * 256 + T[s].col[j] * 64;
+                const uint32_t d = tmem + mine * 256 + T[s].col[j] * 64;
                 const uint32_t id = T[s].n[j] == 4 ? id256 : (T[s].n[j] == 2 ? id128 : id64);
                 const uint32_t bj = smem_desc_lo(smem_a + (j ? b1 : b0) * kT4Gran, 8192);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   umma_bf16_lh(d, a_lo + k * 2, desc_hi, bj + k * (2048 >> 4), desc_hi, id, (first && k == 0) ? 0u : 1u);
               }
+              umma_commit_a(empty_a + bar * 8);
+              first = false;
+            } else {
+              mbar_arrive_a(empty_a + bar * 8);
             }
-            umma_commit_a(empty_a + bar * 8);
-            first = false;
           }
         }
-        if (alive) umma_commit_a(tfull_a);
+        if (alive) {
+          if (active) umma_commit_a(tfull_a);
+          else mbar_arrive_a(tfull_a);
+        }
         ++nseg;
       }
     }
@@ -1589,7 +1604,7 @@ static int tc_dgrad4(const mcg_conv_geom* g, const void* dy, const void* w, void
     if (e != cudaSuccess) MCG_FAIL((int)e, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
     configured = true;
   }
-  pdl(tc_dgrad4_kernel, grid, kTcThreads, kT4Smem, st)(ma, mb, P, dx, bias);
+  pdl(tc_dgrad4_kernel, grid, kT4Threads, kT4Smem, st)(ma, mb, P, dx, bias);
   MCG_CHECK_LAUNCH(who);
   return 0;
 }
