@@ -221,14 +221,19 @@ def time_conv_layers(K, torch, peaks):
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 10
-            e0.record()
-            for _ in range(reps):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / reps
+            # best of 3 batches of 10 back-to-back launches: the burst peak these are divided by is itself a best-of-10
+            # (MEASURED_PEAKS.json "how"), so both sides are the clocks-up figure of a kernel running alone
+            reps, best = 10, None
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                t = e0.elapsed_time(e1) / reps
+                best = t if best is None or t < best else best
+            ms = best
             rows.append({"kernel": "tc_conv_%s" % kind, "layer": name, "ms": ms, "gflop": flops / 1e9,
                          "tflops": flops / ms / 1e9, "calls_per_step": ncalls,
                          "frac_of_burst_peak": flops / ms / 1e9 / peaks["bf16_burst"]})
@@ -522,6 +527,20 @@ def run_ours(args):
     assert identical, "data-parallel replicas diverged"
     exposed = getattr(up, "exposed_collective_ms", None)
 
+    # ---- per-kernel tables (rank 0): every launch timed ALONE, before the long legs below heat the part into its power cap
+    layer_rows, stream_rows, narrow_rows, dominant = None, None, None, None
+    if rank == 0:
+        time.sleep(0.5)
+        layer_rows = time_conv_layers(K, torch, peaks)
+        stream_rows = time_stream_kernels(K, torch, peaks)
+        narrow_rows = time_narrow_layers(K, torch, peaks)
+        tot = {}
+        for r in layer_rows:
+            tot[(r["kernel"], r["layer"])] = r["ms"] * r["calls_per_step"]
+        dk = max(tot, key=tot.get)
+        dominant = [r for r in layer_rows if (r["kernel"], r["layer"]) == dk][0]
+    barrier()
+
     # ---- BASELINE config 4 (infogan) on the same N GPUs, same timing rules
     other = None
     if not args.no_other_model:
@@ -545,18 +564,9 @@ def run_ours(args):
         except ImportError:
             gen128 = None
 
-    layer_rows, stream_rows, narrow_rows, dominant, cpu = None, None, None, None, None
-    if rank == 0:
-        layer_rows = time_conv_layers(K, torch, peaks)
-        stream_rows = time_stream_kernels(K, torch, peaks)
-        narrow_rows = time_narrow_layers(K, torch, peaks)
-        tot = {}
-        for r in layer_rows:
-            tot[(r["kernel"], r["layer"])] = r["ms"] * r["calls_per_step"]
-        dk = max(tot, key=tot.get)
-        dominant = [r for r in layer_rows if (r["kernel"], r["layer"]) == dk][0]
-        if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline_config1()
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_config1()
     if rank != 0:
         return
     steps_per_s = world * args.steps / (ms_dev / 1e3)
