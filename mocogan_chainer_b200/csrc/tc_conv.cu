@@ -67,6 +67,9 @@ struct TcParams {
   int skip_t, skip_per_kt[8], skip_nkt, skip_dt0, skip_dts, skip_aT;   // skip_per_kt: per stride class
   int str_rounds, str_rem_per; long long str_rem0;   // strided: full rounds of groups, then total - str_rem0 left-over units dealt str_rem_per per CTA
   int win, win_T;   // window-view A operand of the 3-channel layers (see TcWin): TMA coordinates (0, w, h, n*win_T + t, 0)
+  // split-K (fprop of layers with too few pixel boxes to fill the machine, e.g. Dv.dc4: 18 boxes): unit = (k split, tile, box);
+  // split ks multiplies taps [ks*ks_taps, (ks+1)*ks_taps) and red.adds its fp32 partial tile into a zeroed scratch tensor
+  int ksplit, ks_taps;
   int strided;  // > 0: CTA c takes the unit groups c, c + grid, c + 2*grid, ... of `strided` units each (boxes cost
                 // different numbers of K steps once taps are skipped; contiguous ranges would be frame-coherent and uneven)
   int box_tn;   // 1: boxes are numbered (w, h, n, t) — frames slowest — so the MT boxes of a step share their frame and skip alike
@@ -125,8 +128,15 @@ struct TcSegIter {
       u += n;
       return true;
     }
-    s.tile = (int)(u / P.nboxes);
-    s.box0 = (int)(u - (long long)s.tile * P.nboxes);
+    long long ur = u;
+    int ks = 0;
+    if (P.ksplit > 1) {
+      const long long per = (long long)P.ntiles * P.nboxes;
+      ks = (int)(u / per);
+      ur = u - ks * per;
+    }
+    s.tile = (int)(ur / P.nboxes);
+    s.box0 = (int)(ur - (long long)s.tile * P.nboxes);
     long long n = P.nboxes - s.box0;
     if (n > u_end - u) n = u_end - u;
     if (n > MT) n = MT;
@@ -134,6 +144,7 @@ struct TcSegIter {
     s.k0 = 0;
     s.j0 = 0;
     s.nk = P.tap_count[s.tile / P.ntn] * P.chunks;
+    if (P.ksplit > 1) { s.j0 = ks * P.ks_taps; s.nk = P.ks_taps * P.chunks; }
     if (P.skip_t) {
       // frames covered by the step's boxes.  box index = ((n*nbt + t)*nbh + h)*nbw + w: a step that crosses into the next
       // sample keeps every tap; with box_tn = ((t*nbb + n)*nbh + h)*nbw + w: frames never wrap inside a step
@@ -363,6 +374,12 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& P, void* __rest
                     *reinterpret_cast<uint2*>(o + plane * P.planar_stride + (long long)ow * P.planar_chunk + within) = u;
                   }
                 }
+              } else if (MODE == kFprop && P.ksplit > 1) {
+                // split-K partial tile: fp32 red.add into the scratch tensor (same strides as y); bias and the cast to
+                // the output type follow in splitk_finish_kernel
+                float* o = reinterpret_cast<float*>(out) + base + c0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) atomicAdd(o + i, f[i]);
               } else if (P.out_f32) {
                 float* o = reinterpret_cast<float*>(out) + base + c0;
 #pragma unroll
@@ -1609,6 +1626,57 @@ static int tc_dgrad4(const mcg_conv_geom* g, const void* dy, const void* w, void
   return 0;
 }
 
+// ---- split-K for fprop ------------------------------------------------------------------------------------------
+// y[m][c] = bias[c] + scratch[m][c], cast to the output type (8 elements per thread; Cout % 8 == 0)
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float4* __restrict__ acc, const float* __restrict__ bias,
+                                                            void* __restrict__ y, int out_f32, long long n8, int C) {
+  pdl_enter();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = acc[2 * i], b = acc[2 * i + 1];
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (bias) {
+      const int c0 = (int)((i * 8) % C);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += bias[c0 + k];
+    }
+    if (out_f32) {
+      float4* o = reinterpret_cast<float4*>(y) + 2 * i;
+      o[0] = make_float4(v[0], v[1], v[2], v[3]);
+      o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+      reinterpret_cast<uint4*>(y)[i] = u;
+    }
+  }
+}
+// A layer whose widest tiles give fewer than half as many work units as there are SMs (Dv.dc4: 2,240 pixels = 18 boxes x 2
+// column tiles of 256) either runs narrow tiles — every pixel box re-read once per column tile, every weight tile once
+// per box: 0.88 GB through L2 for 37.6 GF — or leaves most SMs idle.  Split-K keeps the 128 x 256 tile and cuts the
+// tap loop over S CTAs.  Returns S (1 = no split) for an fprop geometry; the scratch tensor is M x Cout fp32.
+static int splitk_plan(const mcg_conv_geom* g, int wrows) {
+  // OFF unless MCG_TC_SPLITK=1: measured on Dv.dc4 fprop (S = 4, 144 CTAs of 128 x 256 tiles), 0.061 -> 0.078 ms — the 4.6 M
+  // scalar fp32 red.adds of the partial tiles plus the memset and finish launches cost more than the idle SMs did
+  if (!tc_env_int("MCG_TC_SPLITK") || g->Cout % 256 || g->Cin % 64 || (wrows && wrows != g->Cout) || g->pT > 0) return 1;
+  const int taps = g->kT * g->kH * g->kW;
+  const Box bx = choose_box(128, g->Wo, g->Ho, g->To, g->N);
+  const long long nboxes = (long long)ceil_div(g->Wo, bx.w) * ceil_div(g->Ho, bx.h) * ceil_div(g->To, bx.t) * ceil_div(g->N, bx.b);
+  const long long units = nboxes * (g->Cout / 256);
+  const int sms = tc_sms();
+  if (units * 2 > sms) return 1;
+  // the extra memset + finish launches only pay for a layer with real work (Dv.dc4: 37.6 GF; not Di.dc3/dc4: 2.3 GF)
+  if (2.0 * g->N * g->To * g->Ho * g->Wo * (double)g->Cout * g->Cin * taps < 1e10) return 1;
+  int S = 1;
+  while (S < 8 && units * (S * 2) <= sms && taps % (S * 2) == 0 && (taps / (S * 2)) * (g->Cin / 64) >= 16) S *= 2;
+  return S;
+}
+size_t tc_splitk_workspace(const mcg_conv_geom* g) {
+  if (splitk_plan(g, 0) <= 1) return 0;
+  return (size_t)g->N * g->To * g->Ho * g->Wo * g->Cout * sizeof(float) + 256;
+}
+
 bool tc_supported(const mcg_conv_geom* g) {
   if (g->Cin % 64 || g->Cout % 64) return false;
   if (g->sT > 2 || g->sH > 2 || g->sW > 2) return false;
@@ -1619,7 +1687,7 @@ bool tc_supported(const mcg_conv_geom* g) {
 
 int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void* out, const float* bias, int out_dtype,
             cudaStream_t st, int kreal = 0, int planar_chunk = 0, int planar_cols = 0, int wrows = 0, const TcWin* win = nullptr,
-            const int* d2s = nullptr, int store_cols = 0) {   // d2s: {C, sT, sH, sW, Ti, Hi, Wi} -> depth-to-space epilogue (fprop)
+            const int* d2s = nullptr, int store_cols = 0, float* splitk_scratch = nullptr) {   // d2s: {C, sT, sH, sW, Ti, Hi, Wi} -> depth-to-space epilogue (fprop)
   const char* who = mode == kFprop ? "mcg_conv_fprop(tc)" : mode == kDgrad ? "mcg_conv_dgrad(tc)" : "mcg_conv_wgrad(tc)";
   if (!tc_supported(g)) MCG_FAIL(MCG_ERR_UNSUPPORTED, "%s: needs Cin,Cout %% 64 == 0, stride <= 2, <= 64 taps", who);
   TcParams P;
@@ -1679,7 +1747,30 @@ int tc_conv(int mode, const mcg_conv_geom* g, const void* a, const void* b, void
         for (int kw = 0; kw < g->kW; ++kw, ++j) P.taps[j] = TcTap{(int16_t)kw, (int16_t)kh, (int16_t)kt, (int16_t)j};
     P.nboxes = P.nbw * P.nbh * P.nbt * P.nbb;
     double plain_cost = 0;
-    const TileCfg cfg = pick_tile(kFprop, P.nboxes, 1, g->Cout, taps * P.chunks, &plain_cost);
+    TileCfg cfg = pick_tile(kFprop, P.nboxes, 1, g->Cout, taps * P.chunks, &plain_cost);
+    const int S = (splitk_scratch && !planar_chunk && !win && !d2s && !store_cols) ? splitk_plan(g, wrows == g->Cout ? 0 : wrows) : 1;
+    if (S > 1) {
+      // widest tile, tap loop cut S ways; partial tiles meet in the fp32 scratch (zeroed here), then bias + cast
+      cfg = TileCfg{1, 256};
+      P.ksplit = S; P.ks_taps = taps / S;
+      if ((rc = act_map(&ma, a, g->Cin, g->Wi, g->Hi, g->Ti, g->N, bx.w, bx.h, bx.t, bx.b, g->sW, g->sH, g->sT))) return rc;
+      P.ntn = g->Cout / cfg.bn;
+      P.ntiles = P.ntn;
+      const int grid = split_units(P, (long long)S * P.ntiles * P.nboxes, 1);
+      uint64_t d2[2] = {(uint64_t)P.Ktot, (uint64_t)wrows}, s2[1] = {(uint64_t)P.Ktot * 2};
+      uint32_t b2[2] = {64, (uint32_t)cfg.bn}, e2[2] = {1, 1};
+      if ((rc = get_map(&mb, b, 2, d2, s2, b2, e2))) return rc;
+      const long long n = (long long)g->N * g->To * g->Ho * g->Wo * g->Cout;
+      cudaError_t e = cudaMemsetAsync(splitk_scratch, 0, (size_t)n * sizeof(float), st);
+      if (e != cudaSuccess) MCG_FAIL((int)e, "%s: cudaMemsetAsync: %s", who, cudaGetErrorString(e));
+      if ((rc = launch_tc_cfg<kFprop>(cfg, ma, mb, P, grid, splitk_scratch, nullptr, st, who))) return rc;
+      long long nb = (n / 8 + 255) / 256;
+      if (nb > (long long)num_sms() * 8) nb = (long long)num_sms() * 8;
+      pdl(splitk_finish_kernel, (unsigned)nb, 256, 0, st)(reinterpret_cast<const float4*>(splitk_scratch), bias, out, out_dtype == MCG_F32,
+                                                         n / 8, g->Cout);
+      MCG_CHECK_LAUNCH(who);
+      return 0;
+    }
     if (g->kT >= 2 && g->sT == 1 && !planar_chunk && !win) {
       const TrPlan tr = plan_tr(g->Wo, g->Ho, g->To, g->N, g->Cout, 1, g->kH * g->kW, P.chunks, g->kT);
       if (tr_wanted(tr, plain_cost)) {
@@ -2426,6 +2517,7 @@ extern "C" {
 
 size_t mcg_conv_workspace_bytes(const mcg_conv_geom* g, int impl) {
   if (g && (impl & 0xff) == MCG_IMPL_TC && !tc_supported(g) && tc_small_supported(g)) return tc_small_workspace(g);
+  if (g && (impl & 0xff) == MCG_IMPL_TC && tc_supported(g)) return tc_splitk_workspace(g);   // fprop split-K scratch (else 0)
   return 0;
 }
 
@@ -2439,7 +2531,11 @@ int mcg_conv_fprop(const mcg_conv_geom* g, const void* x, const void* w, const f
     if (dtype != MCG_BF16) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_fprop(tc): activations must be bf16");
     if (!tc_supported(g) && tc_small_supported(g))
       return tc_conv_small(0, g, x, w, y, bias, out_dtype, workspace, workspace_bytes, as_stream(stream), cols_valid);
-    return tc_conv(0, g, x, w, y, bias, out_dtype, as_stream(stream), 0, 0, 0, wrows);
+    // split-K needs its scratch tensor; a caller that passes none gets the unsplit kernel
+    float* scratch = nullptr;
+    if (workspace && workspace_bytes >= tc_splitk_workspace(g) && tc_splitk_workspace(g) > 0)
+      scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    return tc_conv(0, g, x, w, y, bias, out_dtype, as_stream(stream), 0, 0, 0, wrows, nullptr, nullptr, 0, scratch);
   }
   if (wrows) MCG_FAIL(MCG_ERR_UNSUPPORTED, "mcg_conv_fprop: MCG_W_ROWS needs MCG_IMPL_TC");
   return simt_conv(0, g, x, nullptr, (const float*)w, bias, y, dtype, out_dtype, 0, as_stream(stream));

@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
+LAYER = sys.argv[3] if len(sys.argv) > 3 else "Dv.dc2"
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
 want = ['gpu__time_duration.sum', 'sm__cycles_elapsed.max', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
@@ -20,7 +21,7 @@ want = ['gpu__time_duration.sum', 'sm__cycles_elapsed.max', 'launch__grid_size',
         'l1tex__m_xbar2l1tex_read_bytes.sum.per_second', 'l1tex__m_l1tex2xbar_write_bytes.sum',
         'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_sector_hit_rate.pct',
         'sm__warps_active.avg.pct_of_peak_sustained_active']
-names = {0: 'tc_conv_fprop:Dv.dc2', 1: 'tc_conv_dgrad:Dv.dc2', 2: 'tc_conv_wgrad:Dv.dc2'}
+names = {0: 'tc_conv_fprop:' + LAYER, 1: 'tc_conv_dgrad:' + LAYER, 2: 'tc_conv_wgrad:' + LAYER}
 
 
 def tobytes(v, u):
@@ -63,11 +64,20 @@ for sec in open(sys.argv[2]).read().split('"Kernel Name",')[1:]:
     out.append('  %s' % kn)
     out.append('     total samples %d; producer code %d samples, %d on `empty` try_wait; MMA-issuer code %d samples, %d on `full` try_wait'
                % (sum(dd[0] for dd in data), pt, pw, mt, mw))
-head = ['ncu --set full --clock-control none --import-source on -k regex:tc_ -s 6 -c 3   on   python tools/profile_conv.py Dv.dc2',
-        '(third round of fprop / dgrad / wgrad of BASELINE config 2\'s Dv.dc2: 93.95 GF each; csrc sha %s; one B200; ncu serialises the' % bench.csrc_sha(),
+head = ['ncu --set full --clock-control none --import-source on -k regex:tc_ -s 6 -c 3   on   python tools/profile_conv.py ' + LAYER,
+        '(third round of fprop / dgrad / wgrad of BASELINE config 2\'s %s; csrc sha %s; one B200; ncu serialises the' % (LAYER, bench.csrc_sha()),
         ' launches and the SMs run ~1.7 GHz under it, so durations are longer than bench.py\'s: read shares and byte counts)', '']
-open(os.path.join(ROOT, 'profiles', 'r02_ncu_dv_dc2.txt'), 'w').write('\n'.join(head + out) + '\n')
-json.dump(dict(traffic, csrc_sha=bench.csrc_sha(),
-               source='profiles/r02_ncu_dv_dc2.txt (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch)'),
-          open(os.path.join(ROOT, 'profiles', 'r02_traffic.json'), 'w'), indent=1)
+tag = LAYER.lower().replace('.', '_')
+open(os.path.join(ROOT, 'profiles', 'r02_ncu_%s.txt' % tag), 'w').write('\n'.join(head + out) + '\n')
+tpath = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+old = {}
+if os.path.exists(tpath):
+    with open(tpath) as f:
+        old = json.load(f)
+if old.get('csrc_sha') != bench.csrc_sha():
+    old = {}
+old.update(traffic)
+old['csrc_sha'] = bench.csrc_sha()
+old['source'] = 'profiles/r02_ncu_<layer>.txt (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch)'
+json.dump(old, open(tpath, 'w'), indent=1)
 print('\n'.join(out[-8:]))

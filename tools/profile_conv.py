@@ -11,7 +11,10 @@ from mocogan_chainer_b200 import kernels as K  # noqa: E402
 
 LAYERS = {"Dv.dc2": (35, 64, 128, (13, 32, 32), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
           "Dv.dc3": (35, 128, 256, (10, 16, 16), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
-          "G.dc3": (560, 128, 256, (1, 16, 16), (1, 4, 4), (1, 2, 2), (0, 1, 1))}
+          "Dv.dc4": (35, 256, 512, (7, 8, 8), (4, 4, 4), (1, 2, 2), (0, 1, 1)),
+          "Di.dc2": (35, 64, 128, (1, 32, 32), (1, 4, 4), (1, 2, 2), (0, 1, 1)),
+          "G.dc3": (560, 128, 256, (1, 16, 16), (1, 4, 4), (1, 2, 2), (0, 1, 1)),
+          "G.dc4": (560, 64, 128, (1, 32, 32), (1, 4, 4), (1, 2, 2), (0, 1, 1))}
 name = sys.argv[1] if len(sys.argv) > 1 else "Dv.dc2"
 N, Cin, Cout, in_sp, k, s, p = LAYERS[name]
 g = K.make_geom(N, Cin, Cout, in_sp, k, s, p)
