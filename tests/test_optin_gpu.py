@@ -1,5 +1,5 @@
-"""The opt-in scheduling paths stay parity-green: programmatic dependent launch (MCG_PDL=1) and dynamic work distribution
-of the persistent fprop/dgrad kernels (MCG_TC_DYN=1).  Both are read once per process, so each case runs in a child
+"""The opt-in paths stay parity-green: programmatic dependent launch (MCG_PDL=1), dynamic work distribution of the
+persistent fprop/dgrad kernels (MCG_TC_DYN=1) and split-K fprop (MCG_TC_SPLITK=1).  Both are read once per process, so each case runs in a child
 pytest process with the flag set: the BASELINE config-2 layer sizes of the tcgen05 kernels against the float64
 host convolution (only those are large enough for the dynamic distribution to switch on) and one whole update_core step
 against the oracle."""
@@ -17,6 +17,8 @@ SELECT = {
     "MCG_PDL": STEP + ["tests/test_step_gpu.py::test_step_fp32_strict_infogan"],
     # the dynamic distribution only switches on when a CTA has >= 4 tile steps: the full-size layers
     "MCG_TC_DYN": ["tests/test_kernels_gpu.py::test_conv_tc_full_size_vs_float64"] + STEP,
+    # split-K fprop (fp32 red.add of partial tiles + finish pass): only Dv.dc4 is large and box-poor enough to take it
+    "MCG_TC_SPLITK": ["tests/test_kernels_gpu.py::test_conv_tc_full_size_vs_float64[Dv.dc4]"],
 }
 
 
