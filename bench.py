@@ -131,7 +131,7 @@ def make_clip_cache(batch, seed, n_videos=70, frames=40):
     return Uint8ClipCache(videos, labels, batch, video_length=16, extract_speed=2, shuffle=True, pin=True)
 
 
-def build_updater(batch, seed, use_graph, model="normal"):
+def build_updater(batch, seed, use_graph, model="normal", no_comm=False):
     import torch
     from mocogan_chainer_b200 import chainer, parallel
     from mocogan_chainer_b200 import random as mrandom
@@ -150,6 +150,9 @@ def build_updater(batch, seed, use_graph, model="normal"):
         o.add_hook(chainer.optimizer.WeightDecay(1e-5), "hook_dec")
         opts[name] = o
     parallel.attach(list(opts.values()))
+    if no_comm:      # timing only: the same step with the gradient collectives taken out (replicas then diverge)
+        for o in opts.values():
+            o.grad_transform = None
     mrandom.set_source(mrandom.DeviceRandom(seed=seed, device="cuda", video_length=16))
     it = PinnedClipIterator(batch, seed)
 
@@ -435,9 +438,9 @@ def max_over_ranks(torch, world, vals):
     return [float(v) for v in tt]
 
 
-def train_leg(torch, K, parallel, args, model, rank, world, barrier, sampler=None):
+def train_leg(torch, K, parallel, args, model, rank, world, barrier, sampler=None, no_comm=False):
     """Builds the three networks + Updater for `model`, captures the step, does W warm-up replays and times K steps."""
-    up, it = build_updater(BATCH, parallel.shard_seed(1234, rank), use_graph=not args.no_graph, model=model)
+    up, it = build_updater(BATCH, parallel.shard_seed(1234, rank), use_graph=not args.no_graph, model=model, no_comm=no_comm)
     x_dev = it.x[0].cuda()
     t_dev = it.t[0].cuda()
     # set-up (not warm-up): one eager step to count our kernel launches per step, then graph_warmup eager steps + capture
@@ -525,7 +528,7 @@ def run_ours(args):
     # ---- replicas: every rank must hold bit-identical parameters after the timed loops (BatchNorm running stats are local)
     identical = parallel.replicas_identical([up.image_gen, up.image_dis, up.video_dis])
     assert identical, "data-parallel replicas diverged"
-    exposed = getattr(up, "exposed_collective_ms", None)
+    exposed = None
 
     # ---- per-kernel tables (rank 0): every launch timed ALONE, before the long legs below heat the part into its power cap
     layer_rows, stream_rows, narrow_rows, dominant = None, None, None, None
@@ -555,6 +558,15 @@ def run_ours(args):
                  "workload": "BASELINE config %s: MoCoGAN %s model, clips (35,3,16,64,64) per GPU" % ("4" if om == "infogan" else "2", om),
                  "gpu_launches_per_step": int(lps2), "replicas_identical": bool(ident2)}
         del up2
+        torch.cuda.empty_cache()
+    # ---- what the collectives cost a step: the same captured step on the same GPUs with the all-reduces taken out
+    if world > 1 and not args.no_other_model:
+        up3, _, _, _, ms3, _, _ = train_leg(torch, K, parallel, args, args.model, rank, world, barrier, no_comm=True)
+        ms3 = max_over_ranks(torch, world, [ms3])[0]
+        exposed = {"ms_per_step_without_collectives": ms3 / args.steps, "exposed_collective_ms": (ms_dev - ms3) / args.steps,
+                   "note": "same run, same GPUs, gradient all-reduces (and their bf16 casts) removed from the captured step; "
+                           "the difference is what the three collectives add to the critical path"}
+        del up3
         torch.cuda.empty_cache()
     gen = gen128 = None
     if not args.no_gen:

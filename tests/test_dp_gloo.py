@@ -47,6 +47,15 @@ def _worker(rank, world, port, out):
         assert torch.equal(a.grad, torch.arange(16, dtype=torch.float32) * 3)      # sum over ranks 1x + 2x
         assert o.grad_scale == 0.5                                                 # mean applied inside Adam
     assert parallel.shard_seed(1234, rank) == 1234 + rank
+    # replicas_identical: bit-level checksums of every model's parameter arena, all-gathered and compared
+    links = [o.target for o in opts]
+    assert parallel.replicas_identical(links)                  # every rank holds rank 0's weights after attach()
+    if rank == 1:
+        links[1].arena().data[5] = torch.nextafter(links[1].arena().data[5], torch.tensor(2.0))   # one ulp on one rank
+    assert not parallel.replicas_identical(links)
+    if rank == 1:
+        a, b = links[0].arena().data[2].clone(), links[0].arena().data[3].clone()
+        links[0].arena().data[2], links[0].arena().data[3] = b, a                                  # (equal values: no change)
     dist.barrier()
     dist.destroy_process_group()
     out.put(rank)
