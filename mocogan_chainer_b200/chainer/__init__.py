@@ -220,10 +220,28 @@ class Variable(object):
                 if isinstance(x, Parameter) and x.accumulates_in_kernel:
                     pass  # the kernel added straight into the parameter's .grad storage
                 else:
-                    grads[id(x)] = _accumulate(grads.get(id(x)), gx)
+                    prev = grads.get(id(x))
+                    if multi and torch.is_tensor(prev) and torch.is_tensor(gx):
+                        # two dense gradients of one variable, possibly produced on different streams: the sum is a
+                        # kernel too, so it runs on this node's stream AFTER the events of everything added so far,
+                        # and the sum's own event replaces them (none of the models reaches this: their only fan-out
+                        # is the lazy VideoGrad, which is a tuple of references, not arithmetic)
+                        with torch.cuda.stream(s):
+                            for (ps, pev) in ready.get(id(x), ()):
+                                if ps != s:
+                                    s.wait_event(pev)
+                            total = prev + gx
+                            ev_sum = torch.cuda.Event()
+                            ev_sum.record(s)
+                        prev.record_stream(s)
+                        carry.extend((prev, gx))
+                        grads[id(x)] = total
+                        ready[id(x)] = [(s, ev_sum)]
+                    else:
+                        grads[id(x)] = _accumulate(prev, gx)
+                        if multi:
+                            ready.setdefault(id(x), []).append((s, ev))
                     keep[id(x)] = x
-                    if multi:
-                        ready.setdefault(id(x), []).append((s, ev))
                     if x.creator_node is None or retain_grad:
                         x._grad = grads[id(x)]
                 if x.creator_node is not None:

@@ -268,3 +268,50 @@ def test_generator128_extension_matches_composed_oracle_ops(dtype_mode, nf, tol)
     assert err < tol, err
     assert abs(G.forward_gflop_per_frame() - 2 * 16 * (60 * 16 * nf + 16 * nf * 8 * nf * 16 + 8 * nf * 4 * nf * 64 + 4 * nf * 2 * nf * 256
                                                          + 2 * nf * nf * 1024 + nf * 3 * 4096) / 1e9) < 1e-9
+
+
+def test_backward_sums_dense_gradients_across_streams():
+    """A variable with two dense consumers whose nodes ran on different streams (chainer.config.branch_streams): the sum
+    of the two gradients waits for both producers and is itself ordered for whoever reads it next."""
+    from mocogan_chainer_b200 import chainer
+    from mocogan_chainer_b200.chainer import FunctionNode, Variable
+
+    class SlowScale(FunctionNode):
+        def __init__(self, k):
+            super(SlowScale, self).__init__()
+            self.k = k
+
+        def forward(self, inputs):
+            return inputs[0] * self.k,
+
+        def backward(self, idx, gys):
+            g = gys[0]
+            for _ in range(200):              # keep this stream busy so an unordered sum would read a stale buffer
+                g = g * 1.0
+            return g * self.k,
+
+    class Sum2(FunctionNode):
+        def forward(self, inputs):
+            return (inputs[0] + inputs[1]).sum(),
+
+        def backward(self, idx, gys):
+            a, b = self.inputs
+            return tuple(torch.ones_like(v.data) for v in (a, b))[:len(idx)]
+
+    old = chainer.config.branch_streams
+    chainer.config.branch_streams = True
+    try:
+        x = Variable(torch.randn(1 << 20, device="cuda"), requires_grad=True)
+        h = SlowScale(1.0).apply((x,))[0]                      # x -> h on the caller's stream
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            a = SlowScale(2.0).apply((h,))[0]                  # consumer 1 of h, on `side`
+        b = SlowScale(3.0).apply((h,))[0]                      # consumer 2 of h, on the caller's stream
+        torch.cuda.current_stream().wait_stream(side)
+        loss = Sum2().apply((a, b))[0]
+        loss.backward()
+        torch.cuda.synchronize()
+        assert torch.equal(x.grad, torch.full_like(x.data, 5.0))
+    finally:
+        chainer.config.branch_streams = old
