@@ -328,3 +328,39 @@ def test_report_keys_and_train_device_rules(monkeypatch):
     assert chainer.get_report()["image_dis/loss"] == 1.5
     with pytest.raises(ValueError):
         train.main(["--synthetic", "4", "--batchsize", "2"])       # default --gpu -1
+
+
+def test_util_to_sequence_and_image_log_writer(tmp_path):
+    """util.py:13-28 `to_sequence` (frames side by side / stacked) and the SummaryWriter stand-in's two methods."""
+    import json
+    from mocogan_chainer_b200 import util
+    video = np.arange(3 * 2 * 4 * 5, dtype=np.uint8).reshape(3, 2, 4, 5)       # (num, channel, height, width)
+    seq = util.to_sequence(video)
+    assert seq.shape == (2, 4, 15) and np.array_equal(seq[:, :, 5:10], video[1])
+    assert util.to_sequence(video, horizontally=False).shape == (2, 12, 5)
+    w = util.ImageLogWriter(tmp_path / "runs")
+    w.add_image("00th frame", np.zeros((3, 8, 8), np.uint8), 3)
+    w.add_image("grey", np.full((1, 8, 8), 0.5, np.float32), 3)               # [0, 1] floats are scaled like tensorboard does
+    w.add_scalar("loss:ImageGenerator", 1.25, 3)
+    assert (tmp_path / "runs" / "00th_frame_000003.png").exists() and (tmp_path / "runs" / "grey_000003.png").exists()
+    rec = json.loads((tmp_path / "runs" / "scalars.jsonl").read_text().strip())
+    assert rec == {"tag": "loss:ImageGenerator", "value": 1.25, "step": 3}
+
+
+def test_bench_traffic_is_reported_only_for_the_profiled_build(tmp_path, monkeypatch):
+    """bench.load_traffic: the committed ncu figures carry the csrc sha of the build they were captured on; a different
+    tree gets `stale` instead of numbers."""
+    import json
+    import bench
+    sha = bench.csrc_sha()
+    assert len(sha) == 16 and sha == bench.csrc_sha()
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    monkeypatch.setattr(bench, "csrc_sha", lambda: sha)
+    (prof / "r02_traffic.json").write_text(json.dumps({"tc_conv_dgrad:Dv.dc2": 1.0, "csrc_sha": sha}))
+    d, name = bench.load_traffic()
+    assert name == "r02_traffic.json" and d["tc_conv_dgrad:Dv.dc2"] == 1.0 and not d.get("stale")
+    (prof / "r02_traffic.json").write_text(json.dumps({"tc_conv_dgrad:Dv.dc2": 1.0, "csrc_sha": "0" * 16}))
+    d, _ = bench.load_traffic()
+    assert d.get("stale") and "tc_conv_dgrad:Dv.dc2" not in d
