@@ -364,3 +364,25 @@ def test_bench_traffic_is_reported_only_for_the_profiled_build(tmp_path, monkeyp
     (prof / "r02_traffic.json").write_text(json.dumps({"tc_conv_dgrad:Dv.dc2": 1.0, "csrc_sha": "0" * 16}))
     d, _ = bench.load_traffic()
     assert d.get("stale") and "tc_conv_dgrad:Dv.dc2" not in d
+
+
+def test_guard_allocator_hands_out_red_zoned_tensors_and_sees_an_overrun():
+    """tests/guard_alloc.py (the bounds check of tests/test_guard_gpu.py) on host tensors: shapes, strides, dtypes and
+    zero-fill are those of the plain call; one byte written past a tensor is reported; torch is restored on exit."""
+    from tests.guard_alloc import GUARD, guarded_allocations
+    plain = torch.empty
+    with guarded_allocations(cuda_only=False) as g:
+        a = torch.empty((3, 5), dtype=torch.float32)
+        b = torch.zeros(7, dtype=torch.bfloat16)
+        like = plain(2, 3, 4).permute(2, 0, 1)
+        c = torch.empty_like(like)
+        assert a.data_ptr() % 128 == 0 and c.stride() == like.stride() and c.shape == like.shape
+        assert float(b.float().abs().sum()) == 0.0 and float(torch.zeros_like(a).abs().sum()) == 0.0
+        a.fill_(1.0)
+        c.fill_(2.0)
+        assert g.check() == 4
+        torch.empty(10)
+        g.buffers[-1][0][GUARD + 40] = 0
+        with pytest.raises(AssertionError, match="1 bytes above"):
+            g.check()
+    assert torch.empty is plain
