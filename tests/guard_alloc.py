@@ -7,6 +7,11 @@ hand out the middle of a larger byte buffer whose first and last GUARD bytes hol
 proves that no kernel wrote outside the tensor it was given: a box that walks past the end of its tensor, an epilogue
 whose row predicate is off by one tile, a workspace sized for another dispatch path all land in a red zone.  Reads
 outside a tensor are not detected (the parity tests catch those through wrong values).
+
+`poison=True` additionally fills every `empty` / `empty_like` payload with 0xFF bytes (NaN as bf16 and fp32, -1 as
+int32) before it is handed out: a kernel that consumes part of a buffer nobody wrote — padded rows or channels, a
+scratch slot, a layout copy's slack — turns the step's losses and weights into NaN instead of depending on whatever
+the caching allocator left there.
 """
 import contextlib
 
@@ -27,9 +32,10 @@ def dense(t):
 
 
 class Guards(object):
-    def __init__(self, cuda_only=True):
+    def __init__(self, cuda_only=True, poison=False):
         self.buffers = []        # (flat uint8 buffer, payload bytes, description)
         self.cuda_only = cuda_only
+        self.poison = poison
 
     def wrap(self, proto, zero):
         """A tensor with proto's shape, strides and dtype inside a fresh red-zoned buffer."""
@@ -43,6 +49,8 @@ class Guards(object):
         mid = flat[GUARD:GUARD + nbytes].view(proto.dtype)
         if zero:
             mid.zero_()
+        elif self.poison:
+            flat[GUARD:GUARD + nbytes].fill_(0xFF)
         self.buffers.append((flat, nbytes, "%s %s" % (tuple(proto.shape), proto.dtype)))
         return mid.as_strided(proto.shape, proto.stride())
 
@@ -63,8 +71,8 @@ class Guards(object):
 
 
 @contextlib.contextmanager
-def guarded_allocations(cuda_only=True):
-    g = Guards(cuda_only)
+def guarded_allocations(cuda_only=True, poison=False):
+    g = Guards(cuda_only, poison)
     orig = {name: getattr(torch, name) for name in ("empty", "zeros", "empty_like", "zeros_like")}
     g._empty = orig["empty"]
 

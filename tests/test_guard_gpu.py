@@ -32,12 +32,14 @@ def _losses_ok(up):
     assert len(losses) == 3 and all(np.isfinite(v) and abs(v) < 1e3 for v in losses.values()), losses
 
 
-@pytest.mark.parametrize("model", ["normal", "infogan"])
-def test_no_write_outside_any_buffer_baseline_batch35(model):
+@pytest.mark.parametrize("model,poison", [("normal", False), ("infogan", False), ("normal", True), ("infogan", True)])
+def test_no_write_outside_any_buffer_baseline_batch35(model, poison):
+    """poison=True: every `torch.empty` payload starts as NaN bytes, so the step must not consume anything it (or a
+    zero-fill) did not write first — losses and all weights stay finite."""
     import bench
     from mocogan_chainer_b200 import kernels as K
     K._ws_cache.clear()                      # scratch of earlier tests was allocated without red zones
-    with guarded_allocations() as g:
+    with guarded_allocations(poison=poison) as g:
         up, it = bench.build_updater(35, 1234, use_graph=False, model=model)
         up.step_host_inputs(it.x[0].cuda(), it.t[0].cuda())       # device-resident batch (bench `value`)
         up.update_core()                                          # iterator -> pinned host batch -> H2D -> step (bench `e2e`)
@@ -46,12 +48,15 @@ def test_no_write_outside_any_buffer_baseline_batch35(model):
         n = g.check()
     assert n > 200, n                        # activations, gradients, arenas, Adam state, scratch: all were guarded
     _losses_ok(up)
+    for o in up.get_all_optimizers().values():
+        assert bool(torch.isfinite(o.target.arena().data).all()), o.target.name
     K._ws_cache.clear()
 
 
+@pytest.mark.parametrize("poison", [False, True])
 @pytest.mark.parametrize("model,dtype_mode,nf,N", [("cgan", "fp32", 16, 3), ("cgan", "bf16", 64, 3), ("infogan", "bf16", 64, 5),
                                                    ("normal", "fp32", 8, 2)])
-def test_no_write_outside_any_buffer_small_odd_sizes(model, dtype_mode, nf, N):
+def test_no_write_outside_any_buffer_small_odd_sizes(model, dtype_mode, nf, N, poison):
     from mocogan_chainer_b200 import chainer, train
     from mocogan_chainer_b200 import kernels as K
     from mocogan_chainer_b200 import random as mrandom
@@ -63,7 +68,7 @@ def test_no_write_outside_any_buffer_small_odd_sizes(model, dtype_mode, nf, N):
     class _It(object):
         epoch, is_new_epoch, epoch_detail = 0, False, 0.0
 
-    with guarded_allocations() as g:
+    with guarded_allocations(poison=poison) as g:
         G, Di, Dv = train.build_models(model, 50, 10, 6, 3, nf, 16, True, 0.2)
         opts = {k: train.make_optimizer(m, 2e-4, 5e-5) for k, m in (("image_gen", G), ("image_dis", Di), ("video_dis", Dv))}
         mrandom.set_source(mrandom.DeviceRandom(seed=7, device="cuda", video_length=16))
@@ -77,4 +82,6 @@ def test_no_write_outside_any_buffer_small_odd_sizes(model, dtype_mode, nf, N):
         assert K.tc_error_flag() == 0
         assert g.check() > 100
     _losses_ok(up)
+    for m in (G, Di, Dv):
+        assert bool(torch.isfinite(m.arena().data).all()), m.name
     K._ws_cache.clear()

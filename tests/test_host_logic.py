@@ -376,7 +376,7 @@ def test_guard_allocator_hands_out_red_zoned_tensors_and_sees_an_overrun():
         b = torch.zeros(7, dtype=torch.bfloat16)
         like = plain(2, 3, 4).permute(2, 0, 1)
         c = torch.empty_like(like)
-        assert a.data_ptr() % 128 == 0 and c.stride() == like.stride() and c.shape == like.shape
+        assert a.data_ptr() % 64 == 0 and c.stride() == like.stride() and c.shape == like.shape
         assert float(b.float().abs().sum()) == 0.0 and float(torch.zeros_like(a).abs().sum()) == 0.0
         a.fill_(1.0)
         c.fill_(2.0)
@@ -386,3 +386,7 @@ def test_guard_allocator_hands_out_red_zoned_tensors_and_sees_an_overrun():
         with pytest.raises(AssertionError, match="1 bytes above"):
             g.check()
     assert torch.empty is plain
+    with guarded_allocations(cuda_only=False, poison=True) as g:       # unwritten payloads read as NaN / -1
+        assert bool(torch.isnan(torch.empty(9)).all()) and bool(torch.isnan(torch.empty(9, dtype=torch.bfloat16).float()).all())
+        assert bool((torch.empty_like(plain(4, dtype=torch.int32)) == -1).all()) and float(torch.zeros(5).sum()) == 0.0
+        assert g.check() == 4
