@@ -203,7 +203,11 @@ def attach(optimizers, group=None):
 
 def describe():
     """The data-parallel configuration in force, for bench.py's `config`."""
-    return {"grad_comm_dtype": grad_comm_dtype(), "buckets": _env_int("MCG_DP_BUCKETS", DEFAULT_BUCKETS), "thin_ctas": _env_int("MCG_DP_THIN_CTAS", DEFAULT_THIN_CTAS),
+    buckets = _env_int("MCG_DP_BUCKETS", DEFAULT_BUCKETS)
+    # GradBuckets reduces slices of the fp32 gradient buffer in place: with buckets on, only the image discriminator's
+    # whole-buffer all-reduce can still go through Bf16GradAllReduce (attach)
+    comm = grad_comm_dtype() if not buckets else "fp32 (bucketed); image_dis %s" % grad_comm_dtype()
+    return {"grad_comm_dtype": comm, "buckets": buckets, "thin_ctas": _env_int("MCG_DP_THIN_CTAS", DEFAULT_THIN_CTAS),
             "sm_reserve": _env_int("MCG_DP_SM_RESERVE", _env_int("MCG_DP_THIN_CTAS", DEFAULT_THIN_CTAS))}
 
 
